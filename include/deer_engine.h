@@ -1,0 +1,177 @@
+/*
+ * deer_engine.h -- C ABI of the B200-native DeeR-VLA multi-exit inference engine.
+ *
+ * The reference (yueyang130/DeeR-VLA) is pure Python: it has NO plugin / FFI interface.
+ * Its drop-in boundary for the per-timestep hot path is the Python call surface
+ *     ModelWrapper.step            robot_flamingo/eval/eval_utils.py:279-490
+ *     MPTFlamingo.forward          robot_flamingo/models/flamingo_mpt.py:308-461
+ *     ExitController.forward       robot_flamingo/models/value_net.py:277-297
+ * Each entry point below names the reference interface it replaces.  Plain pointers and
+ * sizes only; no torch / C++ types; never throws.  All functions return 0 on success and
+ * a negative DEER_E_* code on failure; deer_last_error() gives the message.
+ *
+ * Threading: one ctx per GPU; calls on one ctx must be serialised by the caller (the
+ * reference module is not re-entrant either: flamingo_lm.py:37-44, action_head.py:474).
+ */
+#ifndef DEER_ENGINE_H
+#define DEER_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEER_ABI_VERSION 1
+
+enum {
+  DEER_OK = 0,
+  DEER_E_INVALID = -1,   /* bad argument (mirrors the reference's python asserts) */
+  DEER_E_CUDA = -2,      /* a CUDA call failed */
+  DEER_E_STATE = -3,     /* call order (weights not finalized, thresholds not set ...) */
+  DEER_E_MISSING = -4    /* a required weight was never loaded */
+};
+
+enum { DEER_PREC_BF16 = 0,   /* product path: bf16 operands, tcgen05 tensor cores, fp32 accumulate */
+       DEER_PREC_FP32 = 1 }; /* validation path: fp32 everywhere, CUDA-core GEMMs (slow) */
+
+enum { DEER_GEMM_TCGEN05 = 0, DEER_GEMM_SIMT = 1 };   /* SIMT = debug fallback selector for bf16 */
+
+enum { DEER_THR_L2 = 0, DEER_THR_MEAN = 1, DEER_THR_MAX = 2, DEER_THR_COSINE = 3 }; /* value_net.py:105-117 */
+
+/* deer_step flags */
+#define DEER_FLAG_FULL_DEPTH 1u  /* calibration: ignore thresholds, run to the last enabled exit,
+                                    record delta at every exit (value_net.py:300-399 "generate" use) */
+
+typedef struct deer_ctx deer_ctx;
+
+/* Model + exit configuration.  Mirrors what eval_calvin.py derives from its flags and the
+ * checkpoint (eval_calvin.py:455-540) and passes to create_model_and_transforms
+ * (robot_flamingo/models/factory.py:53-269). */
+typedef struct deer_config {
+  int32_t abi_version;       /* must be DEER_ABI_VERSION */
+  /* vision tower: open_clip ViT (factory.py:109-114) */
+  int32_t image_size, patch, vit_width, vit_layers, vit_heads, vit_mlp;
+  /* perceiver resampler (open_flamingo/src/helpers.py:68-81) */
+  int32_t perc_depth, perc_heads, perc_dim_head, num_latents, perc_ff_mult;
+  /* language model (MPT-1B for 3B flamingo, MPT-7B for 9B flamingo; factory.py:13-26) */
+  int32_t d_model, n_heads, mlp_ratio, vocab;
+  int32_t qk_ln;             /* 1: MPT-1B GPTBlock (attn_qk_ln, ln_1/ln_2/mlp_up/mlp_down names);
+                                0: MPT-7B MPTBlock (norm_1/norm_2/ffn.up_proj/ffn.down_proj) */
+  int32_t alibi_bias_max;
+  int32_t cross_attn_every;  /* flamingo_lm.py:174-176 */
+  int32_t xattn_heads, xattn_dim_head, xattn_ff_mult;   /* helpers.py:236-258 */
+  int32_t media_token_id;    /* flamingo_lm.py:211 */
+  /* exits */
+  int32_t n_layers;          /* layers built = min(ckpt early_exit_layer, max_layer)+1 (eval_calvin.py:529, flamingo_mpt.py:198) */
+  int32_t exit_interval;     /* flamingo_mpt.py:248-250 */
+  int32_t max_layer;         /* --max_layer as given on the CLI (value_net.py:173 derives min(max_layer-1, E[-1])) */
+  int32_t is_mpt_9b;         /* value_net.py:235-236 (only used by the host-side threshold solver) */
+  /* action head (action_head.py:408-491) */
+  int32_t lstm_hidden, lstm_layers, mlp_dim0, mlp_dim1;
+  int32_t threshold_type;    /* DEER_THR_* */
+  int32_t steps_per_stage;   /* value_net.py:285-286 */
+  /* engine sizing */
+  int32_t max_batch;         /* max concurrent episodes per deer_step call (<= 1024) */
+  int32_t max_slots;         /* number of per-episode LSTM state slots the engine owns */
+  int32_t max_seq;           /* max text tokens S (reference: 32, data.py:912-918) */
+  int32_t precision;         /* DEER_PREC_* */
+  int32_t gemm_impl;         /* DEER_GEMM_* (bf16 only) */
+  int32_t debug_taps;        /* 1: keep per-stage copies readable through deer_get_tap */
+  int32_t host_control;      /* 1: read the active count back after every probe (the reference's
+                                per-probe D2H sync, value_net.py:293) and stop launching when 0;
+                                0: fully device-side control flow, no host sync inside a step */
+} deer_config;
+
+typedef struct deer_stats {
+  int64_t kernel_launches_total;      /* kernels of this library launched since create */
+  int64_t kernel_launches_last_step;  /* ... by the most recent deer_step / deer_step_host */
+  int64_t gemm_launches_last_step;
+  double  gemm_flops_last_step;       /* 2*M*N*K summed over GEMM launches with host-known M upper bound */
+  int64_t steps;
+  int64_t weight_bytes;               /* device bytes held by weights */
+  int64_t workspace_bytes;
+} deer_stats;
+
+/* library-level */
+int         deer_abi_version(void);
+const char* deer_build_info(void);            /* arch, compiler, flags */
+const char* deer_last_error(deer_ctx* ctx);   /* ctx may be NULL (creation errors) */
+
+/* lifetime  -- replaces create_model_and_transforms + model.to(device) (factory.py:53, eval_calvin.py:565) */
+int  deer_create(const deer_config* cfg, int device, deer_ctx** out);
+void deer_destroy(deer_ctx* ctx);
+
+/* weights -- replaces load_state_dict of the OpenFlamingo .pt + DeeR .pth (eval_calvin.py:541-578).
+ * `name` is the reference's state-dict key (e.g. "perceiver.layers.0.0.to_q.weight",
+ * "lang_encoder.transformer.blocks.3.decoder_layer.attn.Wqkv.weight", "extra_exit.rnn.layers.0.weight_ih_l0");
+ * a leading "module." (DDP, train_utils.py:631-638) is ignored; unknown names return 1 (skipped, like strict=False).
+ * `data` is a HOST pointer to contiguous fp32. */
+int deer_load_weight(deer_ctx* ctx, const char* name, const float* data, const int64_t* shape, int ndim);
+int deer_finalize_weights(deer_ctx* ctx);     /* checks completeness, packs fused operands, builds TMA descriptors */
+int deer_num_required_weights(deer_ctx* ctx);
+const char* deer_required_weight_name(deer_ctx* ctx, int i);
+
+/* exit controller -- replaces ExitController._set_threshold_value (value_net.py:177-182).
+ * n must equal the number of exits <= min(max_layer-1, E[-1]). */
+int deer_set_thresholds(deer_ctx* ctx, const float* thresholds, int n);
+int deer_num_exits(deer_ctx* ctx);            /* len(model.get_all_exit_idx()), flamingo_mpt.py:268-270 */
+int deer_exit_layer(deer_ctx* ctx, int i);    /* i-th exit's layer index */
+int deer_num_thresholds(deer_ctx* ctx);
+int deer_ctrl_max_layer(deer_ctx* ctx);       /* value_net.py:173 */
+
+/* episode state -- replaces ModelWrapper.reset -> clear_all_exit_memory (eval_utils.py:252-277,
+ * flamingo_mpt.py:292-306): zero the LSTM (h,c) of the given slots (n < 0: all slots). HOST pointer. */
+int deer_reset(deer_ctx* ctx, const int32_t* slots, int n);
+
+/* one action-step for n concurrent episodes -- replaces ModelWrapper.step's model call +
+ * post-processing (eval_utils.py:433-434, 454-477) for each episode independently.
+ *   slots      [n]            which LSTM state each episode uses (distinct)
+ *   rgb,gripper[n,3,H,W] f32  CLIP-normalised frames (what preprocess_image produces, data.py:898-902)
+ *   ids        [n,S] int64    token ids (preprocess_text_calvin, data.py:905-919)
+ *   mask       [n,S] uint8    attention mask (1 = token), right padded
+ *   timesteps  [n] int32      rollout step of each episode (ExitController.set_timestep, value_net.py:274);
+ *                             may be NULL (=0, always a stage boundary)
+ *   static_exit               >=0: the reference's exit_id mode (flamingo_mpt.py:396-405), no probes; -1: dynamic
+ * outputs (any may be NULL):
+ *   pose_out   [n,6]  tanh head output              gripper_out [n] sigmoid head output
+ *   action_out [n,7]  pose ++ (gripper>0.5 ? +1 : -1)   (eval_utils.py:458,464)
+ *   exit_out   [n]    int32 exit layer index        delta_out [n, num_thresholds] (NaN where not evaluated)
+ * deer_step: every array pointer is a DEVICE pointer, work is enqueued on `stream`
+ * (a cudaStream_t), no host synchronisation unless cfg.host_control.
+ * deer_step_host: every array pointer is a HOST pointer (pinned for full speed); copies in,
+ * runs, copies out and synchronises before returning. */
+int deer_step(deer_ctx* ctx, int n, const int32_t* slots, const float* rgb, const float* gripper,
+              const int64_t* ids, const uint8_t* mask, int S, const int32_t* timesteps,
+              int static_exit, uint32_t flags,
+              float* pose_out, float* gripper_out, float* action_out, int32_t* exit_out, float* delta_out,
+              void* stream);
+int deer_step_host(deer_ctx* ctx, int n, const int32_t* slots, const float* rgb, const float* gripper,
+                   const int64_t* ids, const uint8_t* mask, int S, const int32_t* timesteps,
+                   int static_exit, uint32_t flags,
+                   float* pose_out, float* gripper_out, float* action_out, int32_t* exit_out, float* delta_out);
+
+/* introspection for parity tests (the reference exposes .hidden_states / module attributes) */
+int deer_get_state(deer_ctx* ctx, int slot, float* h_out, float* c_out);   /* HOST [layers, hidden] each */
+/* name: "vit" [2n, patches, width] (rgb images then gripper images), "media" [n, 2*latents, width],
+ * "hidden" [n, S, d] (layer = LLM layer index; rows of episodes that exited earlier keep their last value),
+ * "pooled" [n, d].  Requires cfg.debug_taps.  out is a HOST buffer of `capacity` floats; shape_out[4]. */
+int deer_get_tap(deer_ctx* ctx, const char* name, int layer, float* out, int64_t capacity, int64_t* shape_out);
+int deer_get_stats(deer_ctx* ctx, deer_stats* out);
+
+/* single-operator entry points (DEVICE pointers) so that kernels can be parity-tested in isolation.
+ * dtype: 0 = bf16, 1 = fp32 for A/W (and C unless out_f32).   C[M,N] = epi(A[M,K] @ W[N,K]^T).
+ * epilogue: v = acc (+bias[n]); act 0 none / 1 GELU(erf) / 2 QuickGELU / 3 ReLU; v *= *scale (if scale);
+ * v += resid[m,n] (fp32, ldc) (if resid).  m_dev (optional device int) clamps M to *m_dev * m_mul. */
+int deer_op_gemm(int impl, int dtype, const void* A, int lda, const void* W, int ldw, void* C, int ldc,
+                 int M, int N, int K, const float* bias, int act, const float* scale, const float* resid,
+                 int out_f32, const int32_t* m_dev, int m_mul, void* stream);
+/* softmax(scale * Q K^T) V, no mask, head_dim 64, bf16 (impl 0 = tensor-core flash kernel, 1 = SIMT reference;
+ * dtype as above, impl 0 requires bf16).  Q rows: (b*Sq+i)*ldq + h*64, K/V rows: (b*Sk+j)*ldk + h*64. */
+int deer_op_attention(int impl, int dtype, const void* Q, int ldq, const void* K, const void* V, int ldk,
+                      void* O, int ldo, int B, int H, int Sq, int Sk, int head_dim, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEER_ENGINE_H */
