@@ -1,0 +1,252 @@
+// Attention kernels.
+//   * attn_simt_kernel<T>: generic softmax(scale*QK^T + bias, masks)V, one CTA per (query row,
+//     head, batch).  Handles every flavour on the path: ViT (no mask), Perceiver (no mask),
+//     Flamingo gated x-attn (media-time mask classes, helpers.py:205-229) and MPT self-attention
+//     (ALiBi key bias + causal + key padding, mosaic_gpt_3b.py:158-219).  Used for the tiny
+//     S<=32 LLM attentions (negligible FLOPs) and for everything on the fp32 validation path.
+//   * flash_attn_hd64_kernel: bf16 tensor-core (mma.sync m16n8k16) flash attention, head_dim 64,
+//     no mask -- the ViT 257x257 and Perceiver 64x320 attentions, which are the only ones with
+//     meaningful FLOPs (~4% of a step).
+#pragma once
+#include "common.cuh"
+
+struct AttnParams {
+  const void* Q; const void* K; const void* V; void* O;
+  int ldq, ldk, ldv, ldo;        // row strides (elements)
+  int Sq, Sk, H, hd;
+  float scale;
+  int causal;                    // key j visible to query i iff j <= i + (Sk - Sq)
+  const float* alibi_slopes;     // [H] or nullptr: bias = slope_h * (j - (Sk-1))
+  const int* kv_len;             // [B] number of valid (non-pad) keys, or nullptr
+  const uint8_t* qmode;          // [B,Sq] x-attn class: 0 zero output, 1 attend all, 2 uniform; or nullptr
+  int B_host;
+  const int* n_dev;              // dynamic batch (active episodes) or nullptr
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+attn_simt_kernel(AttnParams p) {
+  extern __shared__ float sm[];      // [hd] q, [Sk] scores, [8] red
+  const int i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nb = p.n_dev ? min(*p.n_dev, p.B_host) : p.B_host;
+  if (b >= nb) return;
+  float* sq = sm;
+  float* sc = sm + p.hd;
+  float* red = sc + p.Sk;
+  const T* Q = reinterpret_cast<const T*>(p.Q) + (static_cast<size_t>(b) * p.Sq + i) * p.ldq + h * p.hd;
+  const T* K = reinterpret_cast<const T*>(p.K) + static_cast<size_t>(b) * p.Sk * p.ldk + h * p.hd;
+  const T* V = reinterpret_cast<const T*>(p.V) + static_cast<size_t>(b) * p.Sk * p.ldv + h * p.hd;
+  T* O = reinterpret_cast<T*>(p.O) + (static_cast<size_t>(b) * p.Sq + i) * p.ldo + h * p.hd;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int mode = 1;
+  if (p.qmode) mode = p.qmode[b * p.Sq + i];
+  if (mode == 0) {                                   // text token before any <image>: attention zeroed
+    for (int d = tid; d < p.hd; d += 128) O[d] = from_f32<T>(0.0f);
+    return;
+  }
+  for (int d = tid; d < p.hd; d += 128) sq[d] = to_f32<T>(Q[d]);
+  __syncthreads();
+  const int kvl = p.kv_len ? p.kv_len[b] : p.Sk;
+  const int jmax = p.causal ? (i + (p.Sk - p.Sq)) : (p.Sk - 1);
+  const float slope = p.alibi_slopes ? p.alibi_slopes[h] : 0.0f;
+  // scores: one warp per key, lanes across head_dim (coalesced)
+  for (int j = warp; j < p.Sk; j += 4) {
+    float acc = 0.0f;
+    const T* kr = K + static_cast<size_t>(j) * p.ldk;
+    for (int d = lane; d < p.hd; d += 32) acc += sq[d] * to_f32<T>(kr[d]);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float s = acc * p.scale + slope * static_cast<float>(j - (p.Sk - 1));
+      if (mode == 2) s = 0.0f;                         // every key masked with the same value -> uniform
+      else if (j > jmax || j >= kvl) s = -INFINITY;
+      sc[j] = s;
+    }
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int j = tid; j < p.Sk; j += 128) m = fmaxf(m, sc[j]);
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  float l = 0.0f;
+  for (int j = tid; j < p.Sk; j += 128) {
+    const float e = (sc[j] == -INFINITY) ? 0.0f : expf(sc[j] - m);
+    sc[j] = e;
+    l += e;
+  }
+  l = warp_sum(l);
+  __syncthreads();
+  if (lane == 0) red[4 + warp] = l;
+  __syncthreads();
+  l = red[4] + red[5] + red[6] + red[7];
+  const float inv = 1.0f / l;
+  for (int d = tid; d < p.hd; d += 128) {
+    float acc = 0.0f;
+    for (int j = 0; j < p.Sk; ++j) acc += sc[j] * to_f32<T>(V[static_cast<size_t>(j) * p.ldv + d]);
+    O[d] = from_f32<T>(acc * inv);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// flash attention, bf16, head_dim 64, no mask.  grid (ceil(Sq/64), H, B), 128 threads.
+// Each warp owns 16 query rows; K/V streamed in 64-key tiles through double-buffered smem.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// [64 rows][64 bf16] tile, 16-byte chunks XOR-swizzled by (row & 7) -> conflict-free ldmatrix
+__device__ __forceinline__ int swz(int row, int col) { return row * 64 + ((((col >> 3) ^ (row & 7)) << 3) | (col & 7)); }
+
+__device__ __forceinline__ void flash_load_tile(bf16* s, const bf16* g, int ld, int row0, int nrows_total, int tid) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int c = tid + it * 128;
+    const int r = c >> 3, ch = c & 7;
+    const bool ok = (row0 + r) < nrows_total;
+    const bf16* src = g + static_cast<size_t>(ok ? (row0 + r) : 0) * ld + ch * 8;
+    cp_async16(s + swz(r, ch * 8), src, ok);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+flash_attn_hd64_kernel(const bf16* __restrict__ Qg, int ldq, const bf16* __restrict__ Kg, const bf16* __restrict__ Vg, int ldk,
+                       bf16* __restrict__ Og, int ldo, int Sq, int Sk, float scale_log2) {
+  __shared__ __align__(128) bf16 sQ[64 * 64];
+  __shared__ __align__(128) bf16 sK[2][64 * 64];
+  __shared__ __align__(128) bf16 sV[2][64 * 64];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  const bf16* Q = Qg + static_cast<size_t>(b) * Sq * ldq + h * 64;
+  const bf16* K = Kg + static_cast<size_t>(b) * Sk * ldk + h * 64;
+  const bf16* V = Vg + static_cast<size_t>(b) * Sk * ldk + h * 64;
+  bf16* O = Og + static_cast<size_t>(b) * Sq * ldo + h * 64;
+
+  flash_load_tile(sQ, Q, ldq, q0, Sq, tid);
+  flash_load_tile(sK[0], K, ldk, 0, Sk, tid);
+  flash_load_tile(sV[0], V, ldk, 0, Sk, tid);
+  cp_async_commit();
+  const int ntiles = (Sk + 63) / 64;
+
+  uint32_t qa[4][4];
+  float o[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.0f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < ntiles) {
+      flash_load_tile(sK[buf ^ 1], K, ldk, (t + 1) * 64, Sk, tid);
+      flash_load_tile(sV[buf ^ 1], V, ldk, (t + 1) * 64, Sk, tid);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (t == 0) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int c = kk * 16 + (lane >> 4) * 8;
+        ldsm_x4(qa[kk], sQ + swz(r, c));
+      }
+    }
+    // S = Q K^T  (16 x 64 per warp)
+    float s[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.0f; }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t kb[4];
+        const int r = np * 16 + (lane & 7) + (lane >> 4) * 8;
+        const int c = kk * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4(kb, sK[buf] + swz(r, c));
+        mma_bf16_16816(s[2 * np], qa[kk], kb[0], kb[1]);
+        mma_bf16_16816(s[2 * np + 1], qa[kk], kb[2], kb[3]);
+      }
+    }
+    // online softmax (log2 domain)
+    const int kbase = t * 64;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const int col = kbase + n * 8 + (lane & 3) * 2;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool valid = (col + (e & 1)) < Sk;
+        s[n][e] = valid ? s[n][e] * scale_log2 : -INFINITY;
+      }
+      mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: every tile has >= 1 valid key
+    const float a0 = exp2f(m0 - mn0), a1 = exp2f(m1 - mn1);
+    m0 = mn0; m1 = mn1;
+    float rs0 = 0.0f, rs1 = 0.0f;
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const float p0 = exp2f(s[n][0] - mn0), p1 = exp2f(s[n][1] - mn0);
+      const float p2 = exp2f(s[n][2] - mn1), p3 = exp2f(s[n][3] - mn1);
+      rs0 += p0 + p1; rs1 += p2 + p3;
+      const int kk = n >> 1;
+      if ((n & 1) == 0) { pa[kk][0] = pack_bf16x2(p0, p1); pa[kk][1] = pack_bf16x2(p2, p3); }
+      else              { pa[kk][2] = pack_bf16x2(p0, p1); pa[kk][3] = pack_bf16x2(p2, p3); }
+    }
+    l0 = l0 * a0 + rs0; l1 = l1 * a1 + rs1;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { o[n][0] *= a0; o[n][1] *= a0; o[n][2] *= a1; o[n][3] *= a1; }
+    // O += P V
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t vb[4];
+        const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int c = np * 16 + (lane >> 4) * 8;
+        ldsm_x4_t(vb, sV[buf] + swz(r, c));
+        mma_bf16_16816(o[2 * np], pa[kk], vb[0], vb[1]);
+        mma_bf16_16816(o[2 * np + 1], pa[kk], vb[2], vb[3]);
+      }
+    }
+    __syncthreads();
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int col = n * 8 + (lane & 3) * 2;
+    if (r0 < Sq) *reinterpret_cast<uint32_t*>(O + static_cast<size_t>(r0) * ldo + col) = pack_bf16x2(o[n][0] * i0, o[n][1] * i0);
+    if (r1 < Sq) *reinterpret_cast<uint32_t*>(O + static_cast<size_t>(r1) * ldo + col) = pack_bf16x2(o[n][2] * i1, o[n][3] * i1);
+  }
+}

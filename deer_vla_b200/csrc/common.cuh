@@ -1,0 +1,60 @@
+// Common device helpers for the DeeR B200 engine (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+
+typedef __nv_bfloat16 bf16;
+
+#define DEER_NUM_SMS 148
+
+// ---- scalar conversions ---------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---- activations (exact forms used by the reference) ------------------------------------
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_QUICKGELU = 2, ACT_RELU = 3 };
+
+__device__ __forceinline__ float gelu_erf(float x) {          // nn.GELU() (approximate='none')
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float quick_gelu(float x) {        // open_clip QuickGELU: x*sigmoid(1.702x)
+  return x / (1.0f + __expf(-1.702f * x));
+}
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_GELU) return gelu_erf(v);
+  if (act == ACT_QUICKGELU) return quick_gelu(v);
+  if (act == ACT_RELU) return fmaxf(v, 0.0f);
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---- warp / block reductions ---------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// dynamic row count: rows = min(M_host, *m_dev * m_mul) when m_dev != nullptr
+__device__ __forceinline__ int dyn_rows(int m_host, const int* m_dev, int m_mul) {
+  if (m_dev == nullptr) return m_host;
+  int m = (*m_dev) * m_mul;
+  return m < m_host ? m : m_host;
+}

@@ -1,0 +1,381 @@
+// GEMM kernels:  C[M,N] = epilogue(A[M,K] @ W[N,K]^T)
+//   * gemm_tc_kernel<BN>  -- the product path: persistent, warp-specialised, TMA-fed
+//     (cp.async.bulk.tensor, 128B swizzle) tcgen05.mma with the fp32 accumulator in TMEM
+//     (double buffered so the epilogue of tile i overlaps the main loop of tile i+1).
+//     A and W are both K-major bf16 (activations row-major, nn.Linear weights [out,in]).
+//   * gemm_simt_kernel<T> -- CUDA-core reference used by the fp32 validation path and as
+//     the in-library cross-check of the tensor-core kernel.
+// Both share one epilogue: v = acc (+bias[n]); v = act(v); v *= *scale; v += resid[m,n];
+// store as bf16 or fp32.  M can be clamped on the device (dynamic early exit: the number
+// of still-active episodes lives in device memory).
+#pragma once
+#include "common.cuh"
+
+struct GemmEpi {
+  void* C;             // [M, ldc] bf16 (out_f32=0) or fp32 (out_f32=1); fp32 validation path stores T=float
+  int ldc;
+  int out_f32;
+  const float* bias;   // [N] or nullptr
+  int act;             // ACT_*
+  const float* scale;  // device scalar (e.g. tanh(attn_gate)) or nullptr
+  const float* resid;  // fp32 [M, ldr] or nullptr (may alias C)
+  int ldr;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure (trap), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread for the CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// this warp's 32 TMEM lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread t = lane t)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory operand descriptor (cute::UMMA::SmemDescriptor layout):
+// start_address[0,14)=addr>>4, LBO[16,30)=1 (unused for swizzled K-major), SBO[32,46)=1024B>>4
+// (stride between 8-row groups), version[46,48)=1, layout_type[61,64)=2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format[4,6)=1 (f32), a_format[7,10)=1 (bf16), b_format[10,13)=1 (bf16),
+// a_major[15]=0, b_major[16]=0 (both K-major), n_dim[17,23)=N>>3, m_dim[24,29)=M>>4
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared epilogue: one output row, NV consecutive columns starting at col0
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void epi_store(const GemmEpi& e, float sc, int row, int col0, int N, float (&v)[NV]) {
+  const bool full = (col0 + NV <= N);
+  if (e.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      if (full || col0 + j < N) v[j] += __ldg(e.bias + col0 + j);
+  }
+  if (e.act != ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = apply_act(v[j], e.act);
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) v[j] *= sc;
+  if (e.resid != nullptr) {
+    const float* rp = e.resid + static_cast<size_t>(row) * e.ldr + col0;
+    if (full && (e.ldr & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < NV; j += 4) {
+        float4 r = *reinterpret_cast<const float4*>(rp + j);
+        v[j] += r.x; v[j + 1] += r.y; v[j + 2] += r.z; v[j + 3] += r.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (col0 + j < N) v[j] += rp[j];
+    }
+  }
+  if (e.out_f32) {
+    float* cp = reinterpret_cast<float*>(e.C) + static_cast<size_t>(row) * e.ldc + col0;
+    if (full && (e.ldc & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < NV; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (col0 + j < N) cp[j] = v[j];
+    }
+  } else {
+    bf16* cp = reinterpret_cast<bf16*>(e.C) + static_cast<size_t>(row) * e.ldc + col0;
+    if (NV % 8 == 0 && full && (e.ldc & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j + 8 <= NV; j += 8) {
+        uint4 o;
+        o.x = pack_bf16x2(v[j], v[j + 1]); o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        o.z = pack_bf16x2(v[j + 4], v[j + 5]); o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(cp + j) = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (col0 + j < N) cp[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 GEMM
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct GemmTc {
+  static constexpr int BM = 128;
+  static constexpr int BK = 64;                       // 64 bf16 = one 128B swizzle row
+  static constexpr int UMMA_K = 16;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;            // two accumulator buffers (128 / 256 / 512 columns)
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual 1 KiB alignment
+  static constexpr int THREADS = 192;                 // warp0 TMA, warp1 MMA+TMEM alloc, warps2-5 epilogue
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               int M_host, const int* __restrict__ m_dev, int m_mul, int N, int K, GemmEpi epi) {
+  using G = GemmTc<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G::STAGES * G::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + G::STAGES;
+  uint64_t* tfull_bar = empty_bar + G::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int M = dyn_rows(M_host, m_dev, m_mul);
+  const int m_blocks = (M + G::BM - 1) / G::BM;
+  const int n_blocks = (N + BN - 1) / BN;
+  const int num_tiles = m_blocks * n_blocks;
+  const int num_kb = (K + G::BK - 1) / G::BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < G::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, G::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;    // N fastest: the A tile stays hot in L2
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sa = smem + s * G::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], G::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[s], kb * G::BK, m_blk * G::BM);
+          tma_load_2d(sa + G::A_BYTES, &tmB, &full_bar[s], kb * G::BK, n_blk * BN);
+          if (++s == G::STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(G::BM, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aph ^ 1u);          // epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);                  // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * G::STAGE_BYTES);
+          const uint64_t adesc = make_desc_sw128(a_addr);
+          const uint64_t bdesc = make_desc_sw128(a_addr + G::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < G::BK / G::UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in the (addr>>4) field
+            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);                   // frees the smem stage when these MMAs retire
+          if (++s == G::STAGES) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(&tfull_bar[as]);                    // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue warps: TMEM -> registers -> global =====
+    const int lane_grp = warp & 3;                      // TMEM lane quarter this warp may access
+    const float sc = (epi.scale != nullptr) ? __ldg(epi.scale) : 1.0f;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const int row = m_blk * G::BM + lane_grp * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c * 32;
+        if (row < M && col0 < N) epi_store<32>(epi, sc, row, col0, N, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, G::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SIMT reference GEMM (fp32 accumulate; T = float for the validation path, bf16 for cross-checks)
+// 64x64 tile, 256 threads, 4x4 outputs per thread, K step 16.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ldw, int M_host,
+                 const int* __restrict__ m_dev, int m_mul, int N, int K, GemmEpi epi) {
+  __shared__ float As[16][64 + 1];
+  __shared__ float Ws[16][64 + 1];
+  const int M = dyn_rows(M_host, m_dev, m_mul);
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  if (m0 >= M) return;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int idx = threadIdx.x; idx < 64 * 16; idx += 256) {
+      const int r = idx >> 4, kk = idx & 15;
+      const int gm = m0 + r, gn = n0 + r, gk = k0 + kk;
+      As[kk][r] = (gm < M && gk < K) ? to_f32<T>(A[static_cast<size_t>(gm) * lda + gk]) : 0.0f;
+      Ws[kk][r] = (gn < N && gk < K) ? to_f32<T>(W[static_cast<size_t>(gn) * ldw + gk]) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const float sc = (epi.scale != nullptr) ? __ldg(epi.scale) : 1.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    const int col0 = n0 + tx * 4;
+    if (row < M && col0 < N) {
+      float v[4] = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
+      epi_store<4>(epi, sc, row, col0, N, v);
+    }
+  }
+}

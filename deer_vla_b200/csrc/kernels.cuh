@@ -1,0 +1,475 @@
+// Bandwidth-bound kernels of the DeeR step: patch gather, token assembly, LayerNorm, embedding,
+// max-pool, LSTM cell, head output + exit gate, active-set compaction.
+// Residual streams are fp32; T (bf16 on the product path, float on the validation path) is the
+// GEMM operand type.  Row counts that depend on the number of still-active episodes are read
+// from device memory (n_dev) so that no host synchronisation is needed inside a step.
+#pragma once
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// block reductions (blockDim.x <= 1024, multiple of 32)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : 0.0f;
+  r = warp_sum(r);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// im2col for the 14x14/stride-14 patch-embed conv (open_clip VisionTransformer.conv1, bias-free):
+// out[(img*np + p), k] with k = c*P*P + ky*P + kx  (== conv weight [out,c,ky,kx] flattened), zero
+// padded to Kp.  Image order: all rgb frames, then all gripper frames.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void im2col_kernel(const float* __restrict__ rgb, const float* __restrict__ grip, T* __restrict__ out,
+                              int n, int H, int P, int Kp) {
+  const int g = H / P, np = g * g;
+  const int row = blockIdx.x;                 // 0 .. 2n*np
+  const int img = row / np, p = row % np;
+  const float* src = (img < n ? rgb + static_cast<size_t>(img) * 3 * H * H : grip + static_cast<size_t>(img - n) * 3 * H * H);
+  const int py = p / g, px = p % g;
+  const int K = 3 * P * P;
+  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    float v = 0.0f;
+    if (k < K) {
+      const int c = k / (P * P), rem = k % (P * P), ky = rem / P, kx = rem % P;
+      v = src[(static_cast<size_t>(c) * H + (py * P + ky)) * H + (px * P + kx)];
+    }
+    out[static_cast<size_t>(row) * Kp + k] = from_f32<T>(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm family.  One CTA (128 threads) per row, row kept in registers (D <= 4096), two-pass
+// statistics in fp32, eps 1e-5.
+//   in row r at  in + r*in_ld ;  gamma/beta indexed by (r % groups)*D + j
+//   out row index = (r / gin) * gout + goff + (r % gin)   (gin=0: identity)
+// ---------------------------------------------------------------------------------------------
+struct LnMap { int gin, gout, goff; };
+__device__ __forceinline__ size_t ln_out_row(int r, const LnMap& m) {
+  return m.gin ? static_cast<size_t>(r / m.gin) * m.gout + m.goff + (r % m.gin) : static_cast<size_t>(r);
+}
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(128)
+layernorm_kernel(const TIn* in, int in_ld, LnMap in_map, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 int groups, int D, TOut* out, int out_ld, LnMap map, TOut* out2, int out2_ld,
+                 int relu, int rows_host, const int* __restrict__ n_dev, int n_mul) {
+  __shared__ float red[32];
+  const int rows = dyn_rows(rows_host, n_dev, n_mul);
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const TIn* x = in + ln_out_row(r, in_map) * in_ld;   // (in == out is allowed: the row is held in registers)
+    float v[32];
+    float s = 0.0f;
+#pragma unroll
+    for (int it = 0; it < 32; ++it) {
+      const int j = threadIdx.x + it * 128;
+      v[it] = (j < D) ? to_f32<TIn>(x[j]) : 0.0f;
+      s += v[it];
+    }
+    const float mean = block_sum(s, red) / D;
+    float q = 0.0f;
+#pragma unroll
+    for (int it = 0; it < 32; ++it) {
+      const int j = threadIdx.x + it * 128;
+      const float d = (j < D) ? v[it] - mean : 0.0f;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(block_sum(q, red) / D + 1e-5f);
+    const float* g = gamma + static_cast<size_t>(groups > 1 ? (r % groups) : 0) * D;
+    const float* bt = beta ? beta + static_cast<size_t>(groups > 1 ? (r % groups) : 0) * D : nullptr;
+    TOut* o = out + ln_out_row(r, map) * out_ld;
+    TOut* o2 = out2 ? out2 + static_cast<size_t>(r) * out2_ld : nullptr;
+#pragma unroll
+    for (int it = 0; it < 32; ++it) {
+      const int j = threadIdx.x + it * 128;
+      if (j < D) {
+        float y = (v[it] - mean) * rstd * g[j] + (bt ? bt[j] : 0.0f);
+        if (relu) y = fmaxf(y, 0.0f);
+        o[j] = from_f32<TOut>(y);
+        if (o2) o2[j] = from_f32<TOut>(y);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ViT token assembly + ln_pre: x[img, 0] = cls + pos[0]; x[img, 1+p] = patch[img*np+p] + pos[1+p]; x = ln_pre(x)
+template <typename T>
+__global__ void __launch_bounds__(128)
+vit_assemble_kernel(const T* __restrict__ patch, const float* __restrict__ cls, const float* __restrict__ pos,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ x,
+                    int n_img, int L, int D) {
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  const int img = r / L, tok = r % L;
+  float v[8];
+  float s = 0.0f;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int j = threadIdx.x + it * 128;
+    float t = 0.0f;
+    if (j < D) {
+      t = (tok == 0) ? cls[j] : to_f32<T>(patch[(static_cast<size_t>(img) * (L - 1) + (tok - 1)) * D + j]);
+      t += pos[static_cast<size_t>(tok) * D + j];
+    }
+    v[it] = t;
+    s += t;
+  }
+  const float mean = block_sum(s, red) / D;
+  float q = 0.0f;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int j = threadIdx.x + it * 128;
+    const float d = (j < D) ? v[it] - mean : 0.0f;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(block_sum(q, red) / D + 1e-5f);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int j = threadIdx.x + it * 128;
+    if (j < D) x[static_cast<size_t>(r) * D + j] = (v[it] - mean) * rstd * gamma[j] + beta[j];
+  }
+}
+
+// drop CLS: tokens[img, p, :] (T) = x[img, 1+p, :]   (perceiver media input; open_clip tokens = x[:,1:])
+__global__ void vit_tokens_kernel(const float* __restrict__ x, float* __restrict__ tok_f32, int n_img, int L, int D) {
+  const size_t total = static_cast<size_t>(n_img) * (L - 1) * D;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int j = i % D;
+    const size_t rp = i / D;
+    const int p = rp % (L - 1);
+    const size_t img = rp / (L - 1);
+    tok_f32[i] = x[(img * L + 1 + p) * D + j];
+  }
+}
+
+// latents[img, :, :] = perceiver.latents (helpers.py:128)
+__global__ void broadcast_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t per, size_t total) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = src[i % per];
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-step episode bookkeeping
+// ---------------------------------------------------------------------------------------------
+struct EpisodeMeta {          // all arrays sized max_batch; "r" = rank inside the current active set
+  int* orig;                  // r -> index in this call's batch
+  int* slot;                  // r -> LSTM state slot
+  int* valid_len;             // r -> number of real tokens
+  uint8_t* xmode;             // [r, S] x-attn class per token (0 no media yet, 1 attend, 2 more than one <image>)
+  float* prev_pose;           // [r, 6] previous exit's pose
+  uint8_t* use_prev;          // r -> 1 when timestep % steps_per_stage != 0 (reuse cur_exit_id, value_net.py:285)
+};
+
+__global__ void init_episodes_kernel(EpisodeMeta m, int* n_active, const int* __restrict__ slots, const int64_t* __restrict__ ids,
+                                     const uint8_t* __restrict__ mask, const int* __restrict__ timesteps, int n, int S,
+                                     int media_id, int sps, int n_thr, int* __restrict__ exit_dev, float* __restrict__ delta_dev) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r == 0) *n_active = n;
+  if (r >= n) return;
+  m.orig[r] = r;
+  m.slot[r] = slots[r];
+  int vl = 0, tt = 0;
+  for (int s = 0; s < S; ++s) {
+    vl += mask[r * S + s] ? 1 : 0;
+    tt += (ids[r * S + s] == media_id) ? 1 : 0;                  // text_time = cumsum(media_locations), helpers.py:208
+    m.xmode[r * S + s] = static_cast<uint8_t>(tt > 2 ? 2 : tt);
+  }
+  m.valid_len[r] = vl;
+  m.use_prev[r] = (timesteps != nullptr && sps > 1 && (timesteps[r] % sps) != 0) ? 1 : 0;
+  exit_dev[r] = -1;
+  for (int k = 0; k < n_thr; ++k) delta_dev[r * n_thr + k] = __int_as_float(0x7fc00000);
+}
+
+// x[r*S+s, :] = wte[ids[r,s], :]   (mosaic_gpt_3b.py:341-343; ALiBi => no position embedding)
+template <typename T>
+__global__ void embed_kernel(const int64_t* __restrict__ ids, const T* __restrict__ wte, float* __restrict__ x, int rows, int D, int vocab) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  long long id = ids[r];
+  if (id < 0) id = 0;
+  if (id >= vocab) id = vocab - 1;
+  const T* w = wte + static_cast<size_t>(id) * D;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) x[static_cast<size_t>(r) * D + j] = to_f32<T>(w[j]);
+}
+
+// AdaptiveMaxPool1d(1) over the (valid) token positions (action_head.py:519-520) -> T row of the LSTM input buffer
+template <typename T>
+__global__ void maxpool_kernel(const float* __restrict__ x, const int* __restrict__ valid_len, T* __restrict__ out, int out_ld,
+                               float* __restrict__ out_f32, int S, int D, int n_host, const int* __restrict__ n_dev) {
+  const int n = dyn_rows(n_host, n_dev, 1);
+  const int r = blockIdx.y;
+  if (r >= n) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= D) return;
+  const int vl = valid_len[r];
+  float m = -INFINITY;
+  for (int s = 0; s < vl; ++s) m = fmaxf(m, x[(static_cast<size_t>(r) * S + s) * D + j]);
+  out[static_cast<size_t>(r) * out_ld + j] = from_f32<T>(m);
+  if (out_f32) out_f32[static_cast<size_t>(r) * D + j] = m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LSTM (LayerNormLSTM, action_head.py:15-64): per layer  gates = [x | h_prev] @ [W_ih | W_hh]^T + (b_ih+b_hh)
+// ---------------------------------------------------------------------------------------------
+// copy the carried h of every layer into the GEMM A operands: A_l[r, in_l + j] = h_state[slot[r], l, j]
+template <typename T>
+__global__ void lstm_gather_h_kernel(const float* __restrict__ h_state, const int* __restrict__ slot, T* __restrict__ a0, int ld0, int off0,
+                                     T* __restrict__ a_rest, int ld_rest, int layers, int Hh, int nstride, int n_host, const int* __restrict__ n_dev) {
+  const int n = dyn_rows(n_host, n_dev, 1);
+  const int r = blockIdx.x, l = blockIdx.y;
+  if (r >= n) return;
+  const float* h = h_state + (static_cast<size_t>(slot[r]) * layers + l) * Hh;
+  T* dst = (l == 0) ? a0 + static_cast<size_t>(r) * ld0 + off0
+                    : a_rest + (static_cast<size_t>(l - 1) * nstride + r) * ld_rest + Hh;
+  for (int j = threadIdx.x; j < Hh; j += blockDim.x) dst[j] = from_f32<T>(h[j]);
+}
+
+// LSTM cell pointwise (gate order i,f,g,o) + LayerNorm(h') -> next layer's x (T).  One CTA (256 thr) per episode.
+template <typename T>
+__global__ void __launch_bounds__(256)
+lstm_cell_kernel(const float* __restrict__ gates, const float* __restrict__ c_state, const int* __restrict__ slot, int layer, int layers,
+                 float* __restrict__ cand_h, float* __restrict__ cand_c, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 T* __restrict__ y, int y_ld, int Hh, int nstride, int n_host, const int* __restrict__ n_dev) {
+  __shared__ float red[32];
+  const int n = dyn_rows(n_host, n_dev, 1);
+  const int r = blockIdx.x;
+  if (r >= n) return;
+  const float* g = gates + static_cast<size_t>(r) * 4 * Hh;
+  const float* cp = c_state + (static_cast<size_t>(slot[r]) * layers + layer) * Hh;
+  float hv[8];
+  float s = 0.0f;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int j = threadIdx.x + it * 256;
+    float h2 = 0.0f;
+    if (j < Hh) {
+      const float ig = sigmoidf_(g[j]), fg = sigmoidf_(g[Hh + j]), gg = tanhf(g[2 * Hh + j]), og = sigmoidf_(g[3 * Hh + j]);
+      const float c2 = fg * cp[j] + ig * gg;
+      h2 = og * tanhf(c2);
+      cand_c[(static_cast<size_t>(layer) * nstride + r) * Hh + j] = c2;
+      cand_h[(static_cast<size_t>(layer) * nstride + r) * Hh + j] = h2;
+    }
+    hv[it] = h2;
+    s += h2;
+  }
+  const float mean = block_sum(s, red) / Hh;
+  float q = 0.0f;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int j = threadIdx.x + it * 256;
+    const float d = (j < Hh) ? hv[it] - mean : 0.0f;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(block_sum(q, red) / Hh + 1e-5f);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int j = threadIdx.x + it * 256;
+    if (j < Hh) y[static_cast<size_t>(r) * y_ld + j] = from_f32<T>((hv[it] - mean) * rstd * gamma[j] + beta[j]);
+  }
+}
+
+// final Linear(+tanh / sigmoid) of both MLP heads (action_head.py:114-116, 215-217).
+// y2 [n, 2*d1] fp32 (pose half | gripper half).  One CTA of 256 threads per episode: warp k<6 -> pose_k, warp 6 -> gripper.
+__global__ void __launch_bounds__(256)
+head_out_kernel(const float* __restrict__ y2, int d1, const float* __restrict__ w_pose, const float* __restrict__ b_pose,
+                const float* __restrict__ w_grip, const float* __restrict__ b_grip, float* __restrict__ pose, float* __restrict__ grip,
+                int n_host, const int* __restrict__ n_dev) {
+  const int n = dyn_rows(n_host, n_dev, 1);
+  const int r = blockIdx.x;
+  if (r >= n) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp > 6) return;
+  const float* x = y2 + static_cast<size_t>(r) * 2 * d1 + (warp == 6 ? d1 : 0);
+  const float* w = (warp == 6) ? w_grip : w_pose + static_cast<size_t>(warp) * d1;
+  float acc = 0.0f;
+  for (int j = lane; j < d1; j += 32) acc += x[j] * w[j];
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    if (warp == 6) grip[r] = sigmoidf_(acc + b_grip[0]);
+    else pose[r * 6 + warp] = tanhf(acc + b_pose[warp]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the exit gate (ExitController.forward value_net.py:277-297 + ActionValueNet get_delta 105-117) for every
+// active episode at once, followed by the survivor scan.  Single CTA of 1024 threads (max_batch <= 1024).
+// ---------------------------------------------------------------------------------------------
+struct GateParams {
+  int layer;                 // LLM layer index of this exit
+  int exit_idx;              // index into thresholds / delta columns (-1: no threshold for this exit)
+  int forced;                // layer >= ctrl_max_layer (value_net.py:293) or static exit
+  int full_depth;            // calibration: never exit before `forced`
+  int has_prev;              // 0: static exit mode, no delta
+  int threshold_type;
+  int n_thr;
+  const float* thresholds;   // device [n_thr]
+  const float* cur_pose;     // [r,6]
+  const float* cur_grip;     // [r]
+  int* cur_exit_id;          // [slots] value_net.py:294
+  // outputs indexed by orig
+  float* pose_out; float* grip_out; float* action_out; int* exit_out; float* delta_out;
+  // compaction
+  uint8_t* exit_flag;        // [r] this episode leaves now
+  int* src_of_new;           // [r'] source rank of survivor r'
+};
+
+__global__ void __launch_bounds__(1024)
+exit_gate_kernel(GateParams g, EpisodeMeta m, const int* __restrict__ n_cur, int* __restrict__ n_next) {
+  __shared__ int wsum[32];
+  __shared__ int total;
+  const int n = *n_cur;
+  const int r = threadIdx.x;
+  int survive = 0;
+  if (r < n) {
+    const float* cp = g.cur_pose + r * 6;
+    float delta = 0.0f;
+    if (g.has_prev) {
+      const float* pp = m.prev_pose + r * 6;
+      if (g.threshold_type == 3) {                                  // cosine (value_net.py:13-21,114)
+        float n1 = 0.f, n2 = 0.f, dp = 0.f;
+        for (int k = 0; k < 6; ++k) { n1 += cp[k] * cp[k]; n2 += pp[k] * pp[k]; dp += cp[k] * pp[k]; }
+        delta = 1.0f - dp / (fmaxf(sqrtf(n1), 1e-5f) * fmaxf(sqrtf(n2), 1e-5f));
+      } else {
+        float acc = 0.0f;
+        for (int k = 0; k < 6; ++k) {
+          const float d = fabsf(cp[k] - pp[k]);
+          if (g.threshold_type == 0) acc += d * d;
+          else if (g.threshold_type == 1) acc += d;
+          else acc = fmaxf(acc, d);
+        }
+        delta = (g.threshold_type == 0) ? sqrtf(acc / 6.0f) : (g.threshold_type == 1 ? acc / 6.0f : acc);
+      }
+    }
+    const int o = m.orig[r];
+    const int sl = m.slot[r];
+    bool ex;
+    if (g.full_depth) {
+      ex = g.forced != 0;
+      if (g.exit_idx >= 0 && g.delta_out) g.delta_out[o * g.n_thr + g.exit_idx] = delta;
+    } else if (m.use_prev[r]) {
+      ex = g.layer >= g.cur_exit_id[sl];                            // value_net.py:285-286
+    } else {
+      if (g.exit_idx >= 0 && g.has_prev && g.delta_out) g.delta_out[o * g.n_thr + g.exit_idx] = delta;
+      const bool leq = (g.exit_idx >= 0 && g.has_prev) ? (delta <= g.thresholds[g.exit_idx]) : false;
+      ex = leq || g.forced;
+      if (ex) g.cur_exit_id[sl] = g.layer;                          // value_net.py:294
+    }
+    if (ex) {
+      const float gr = g.cur_grip[r];
+      if (g.pose_out) for (int k = 0; k < 6; ++k) g.pose_out[o * 6 + k] = cp[k];
+      if (g.grip_out) g.grip_out[o] = gr;
+      if (g.action_out) {                                           // eval_utils.py:458,464
+        for (int k = 0; k < 6; ++k) g.action_out[o * 7 + k] = cp[k];
+        g.action_out[o * 7 + 6] = (gr > 0.5f) ? 1.0f : -1.0f;
+      }
+      if (g.exit_out) g.exit_out[o] = g.layer;
+    }
+    g.exit_flag[r] = ex ? 1 : 0;
+    survive = ex ? 0 : 1;
+  }
+  // exclusive scan of `survive` over the CTA
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = survive;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = wsum[lane];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    wsum[lane] = wi - w;
+    if (lane == 31) total = wi;
+  }
+  __syncthreads();
+  const int pos = wsum[warp] + incl - survive;
+  if (survive) g.src_of_new[pos] = r;
+  if (threadIdx.x == 0) *n_next = total;
+}
+
+// commit the candidate LSTM state of the episodes that exit now (update_hidden_state=True, action_head.py:554-556)
+__global__ void commit_state_kernel(const uint8_t* __restrict__ exit_flag, const int* __restrict__ slot, const float* __restrict__ cand_h,
+                                    const float* __restrict__ cand_c, float* __restrict__ h_state, float* __restrict__ c_state,
+                                    int layers, int Hh, int nstride, int n_host, const int* __restrict__ n_dev) {
+  const int n = dyn_rows(n_host, n_dev, 1);
+  const int r = blockIdx.x, l = blockIdx.y;
+  if (r >= n || !exit_flag[r]) return;
+  const size_t src = (static_cast<size_t>(l) * nstride + r) * Hh;
+  const size_t dst = (static_cast<size_t>(slot[r]) * layers + l) * Hh;
+  for (int j = threadIdx.x; j < Hh; j += blockDim.x) {
+    h_state[dst + j] = cand_h[src + j];
+    c_state[dst + j] = cand_c[src + j];
+  }
+}
+
+// gather survivors into the other half of the ping-pong buffers
+template <typename T>
+__global__ void compact_kernel(const int* __restrict__ src_of_new, const float* __restrict__ x_in, float* __restrict__ x_out, size_t x_per,
+                               const T* __restrict__ media_in, T* __restrict__ media_out, size_t media_per,
+                               EpisodeMeta mi, EpisodeMeta mo, const float* __restrict__ cur_pose, int S,
+                               int n_host, const int* __restrict__ n_next) {
+  const int n = dyn_rows(n_host, n_next, 1);
+  const int r2 = blockIdx.x;
+  if (r2 >= n) return;
+  const int r = src_of_new[r2];
+  const float4* xi = reinterpret_cast<const float4*>(x_in + static_cast<size_t>(r) * x_per);
+  float4* xo = reinterpret_cast<float4*>(x_out + static_cast<size_t>(r2) * x_per);
+  for (size_t i = blockIdx.y * static_cast<size_t>(blockDim.x) + threadIdx.x; i < x_per / 4; i += static_cast<size_t>(gridDim.y) * blockDim.x) xo[i] = xi[i];
+  const uint4* mi4 = reinterpret_cast<const uint4*>(media_in + static_cast<size_t>(r) * media_per);
+  uint4* mo4 = reinterpret_cast<uint4*>(media_out + static_cast<size_t>(r2) * media_per);
+  const size_t mvec = media_per * sizeof(T) / 16;
+  for (size_t i = blockIdx.y * static_cast<size_t>(blockDim.x) + threadIdx.x; i < mvec; i += static_cast<size_t>(gridDim.y) * blockDim.x) mo4[i] = mi4[i];
+  if (blockIdx.y == 0) {
+    if (threadIdx.x == 0) {
+      mo.orig[r2] = mi.orig[r];
+      mo.slot[r2] = mi.slot[r];
+      mo.valid_len[r2] = mi.valid_len[r];
+      mo.use_prev[r2] = mi.use_prev[r];
+    }
+    if (threadIdx.x < 6) mo.prev_pose[r2 * 6 + threadIdx.x] = cur_pose[r * 6 + threadIdx.x];   // action_list[-1], value_net.py:127
+    for (int s = threadIdx.x; s < S; s += blockDim.x) mo.xmode[r2 * S + s] = mi.xmode[r * S + s];
+  }
+}
+
+// prev_pose[r] = pose[r]  (first exit: pseudo previous action from the previous layer's features, value_net.py:122-125)
+__global__ void copy_pose_kernel(const float* __restrict__ pose, float* __restrict__ prev_pose, int n_host, const int* __restrict__ n_dev) {
+  const int n = dyn_rows(n_host, n_dev, 1);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * 6) prev_pose[i] = pose[i];
+}
+
+// debug taps: dst[orig[r], :] = src[r, :]
+template <typename TSrc>
+__global__ void tap_scatter_kernel(const TSrc* __restrict__ src, float* __restrict__ dst, const int* __restrict__ orig, size_t per,
+                                   int n_host, const int* __restrict__ n_dev) {
+  const int n = dyn_rows(n_host, n_dev, 1);
+  const int r = blockIdx.x;
+  if (r >= n) return;
+  const size_t o = orig ? orig[r] : r;
+  for (size_t i = blockIdx.y * static_cast<size_t>(blockDim.x) + threadIdx.x; i < per; i += static_cast<size_t>(gridDim.y) * blockDim.x)
+    dst[o * per + i] = to_f32<TSrc>(src[static_cast<size_t>(r) * per + i]);
+}
+
+// fp32 -> T conversion (weight packing)
+template <typename T>
+__global__ void convert_kernel(const float* __restrict__ src, T* __restrict__ dst, size_t rows, size_t cols, size_t src_ld, size_t dst_ld, size_t dst_col_off) {
+  const size_t total = rows * cols;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = i / cols, c = i % cols;
+    dst[r * dst_ld + dst_col_off + c] = from_f32<T>(src[r * src_ld + c]);
+  }
+}

@@ -1,0 +1,116 @@
+"""Single-kernel parity through the C ABI (deer_op_gemm / deer_op_attention) against torch fp32."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_gemm(A, W, bias, act, scale, resid):
+    v = A.float() @ W.float().t()
+    if bias is not None:
+        v = v + bias
+    if act == 1:
+        v = torch.nn.functional.gelu(v)
+    elif act == 2:
+        v = v * torch.sigmoid(1.702 * v)
+    elif act == 3:
+        v = torch.relu(v)
+    if scale is not None:
+        v = v * scale
+    if resid is not None:
+        v = v + resid
+    return v
+
+
+SHAPES = [(128, 256, 64), (128, 64, 128), (200, 512, 1024), (1000, 3072, 1024), (1028, 1024, 4096),
+          (32, 6144, 2048), (7, 4096, 3072), (300, 200, 136), (5000, 4096, 1024), (1, 6, 512), (38000, 1024, 640)]
+
+
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_plain(impl, M, N, K):
+    from deer_vla_b200.engine import op_gemm
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    out = op_gemm(A, W, out_f32=True, impl=impl)
+    torch.cuda.synchronize()
+    ref = _ref_gemm(A, W, None, 0, None, None)
+    err = (out - ref).abs().max().item()
+    tol = 2e-3 * math.sqrt(K / 64) * 0.5
+    assert err <= tol, f"{impl} {M}x{N}x{K}: max abs err {err} > {tol}"
+
+
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_gemm_epilogues(impl, act):
+    from deer_vla_b200.engine import op_gemm
+    M, N, K = 777, 1000, 512
+    g = torch.Generator(device="cuda").manual_seed(act)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    scale = torch.tensor([0.4621], device="cuda")
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    # bf16 output, bias + act
+    out = op_gemm(A, W, bias=bias, act=act, impl=impl)
+    ref = _ref_gemm(A, W, bias, act, None, None)
+    assert (out.float() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
+    # fp32 residual stream update with the tanh(gate) scale
+    out = op_gemm(A, W, bias=bias, act=act, scale=scale, resid=resid, impl=impl)
+    ref = _ref_gemm(A, W, bias, act, scale, resid)
+    assert (out - ref).abs().max().item() <= 2e-3
+
+
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+def test_gemm_dynamic_m_and_strides(impl):
+    from deer_vla_b200.engine import op_gemm
+    g = torch.Generator(device="cuda").manual_seed(11)
+    big = (torch.randn(640, 2048, device="cuda", generator=g) * 0.5).bfloat16()
+    A = big[:, 1024:1536]                       # lda 2048, column offset: the head MLP reads one half of y1 like this
+    W = (torch.randn(512, 512, device="cuda", generator=g) * 0.05).bfloat16()
+    m_dev = torch.tensor([9], dtype=torch.int32, device="cuda")
+    out = op_gemm(A, W, out_f32=True, impl=impl, m_dev=m_dev, m_mul=32)     # only 9*32 = 288 rows are live
+    ref = _ref_gemm(A, W, None, 0, None, None)
+    assert (out[:288] - ref[:288]).abs().max().item() <= 2e-3
+    assert out[288:].abs().max().item() == 0.0                              # rows past the device-side count untouched
+
+
+def test_gemm_fp32_simt():
+    from deer_vla_b200.engine import op_gemm
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(130, 300, device="cuda", generator=g)
+    W = torch.randn(70, 300, device="cuda", generator=g) * 0.1
+    out = op_gemm(A, W, impl="simt")
+    assert (out - A @ W.t()).abs().max().item() <= 1e-4
+
+
+def _ref_attn(q, k, v, scale):
+    s = torch.einsum("bihd,bjhd->bhij", q.float(), k.float()) * scale
+    return torch.einsum("bhij,bjhd->bihd", s.softmax(-1), v.float())
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk", [(3, 4, 257, 257), (2, 8, 64, 320), (1, 2, 17, 17), (2, 16, 130, 70)])
+@pytest.mark.parametrize("impl", ["flash", "simt"])
+def test_attention_hd64(impl, B, H, Sq, Sk):
+    from deer_vla_b200.engine import op_attention
+    g = torch.Generator(device="cuda").manual_seed(B + H + Sq)
+    q = torch.randn(B, Sq, H, 64, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B, Sk, H, 64, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Sk, H, 64, device="cuda", generator=g).bfloat16()
+    out = op_attention(q, k, v, 0.125, impl=impl)
+    torch.cuda.synchronize()
+    ref = _ref_attn(q, k, v, 0.125)
+    assert (out.float() - ref).abs().max().item() <= 2e-2
+
+
+def test_attention_fp32_simt():
+    from deer_vla_b200.engine import op_attention
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q = torch.randn(2, 33, 3, 128, device="cuda", generator=g)
+    k = torch.randn(2, 50, 3, 128, device="cuda", generator=g)
+    v = torch.randn(2, 50, 3, 128, device="cuda", generator=g)
+    out = op_attention(q, k, v, 1 / math.sqrt(128), impl="simt")
+    assert (out - _ref_attn(q, k, v, 1 / math.sqrt(128))).abs().max().item() <= 1e-4
