@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""DeeR-VLA action-steps/sec benchmark (BASELINE.json metric) -- driver contract in the task brief.
+
+  python bench.py --gpus N --steps K --warmup W            # engine arm (hand-written sm_100a path)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+
+One "step" = one action-step for every one of the B concurrent episodes on a GPU (B = --batch, default 224:
+BASELINE.json "224-seq batch").  value = action-steps/s over all ranks, device-timed with CUDA events,
+inputs resident in HBM.  e2e = the same through DeerEngine.step with HOST (pinned) buffers: H2D of both
+frames + tokens and D2H of actions/exit ids inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+WORKLOADS = {
+    # name: (max_layer, exit_ratio, description)      README.md:124 (12 = DeeR-B, 4 = DeeR-S), README.md:110-122
+    "deer_b": (12, 1.0, "OpenFlamingo-3B DeeR-B max_layer=12 exit_ratio=1.0"),
+    "deer_s": (4, 0.8, "OpenFlamingo-3B DeeR-S max_layer=4 exit_ratio=0.8"),
+}
+
+
+def algorithmic_gflop_per_step(exit_layer: int, exit_rank: int) -> float:
+    """SURVEY.md §8(d) / BASELINE.md §3: 347.0 + 5.79*(e+1) + 0.082*(k+3) GFLOP for an episode exiting at E[k]=e."""
+    return 347.0 + 5.79 * (exit_layer + 1) + 0.082 * (exit_rank + 3)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.stop_flag, self.t = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.t:
+            self.t.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1362.6), d.get("hbm_gbs", 6555.5), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path, batch 1, fp32, all host threads
+# ---------------------------------------------------------------------------------------------------
+def run_cpu_reference(workload: str, steps: int, warmup: int, S: int):
+    from oracle import deer_oracle as O      # the one place bench.py executes oracle/: as the timed CPU baseline
+    max_layer, exit_ratio, desc = WORKLOADS[workload]
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.config_3b(max_layer)
+    W = O.synth_weights(cfg, 0)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "full3b.npz"))
+    thr = gold["thresholds_B" if workload == "deer_b" else "thresholds_S"].tolist()
+    orc = O.DeerOracle(cfg, W, thr)
+    orc.reset()
+    ids = O.synth_tokens(cfg, 0, S)
+    exits = []
+    t0 = None
+    for t in range(warmup + steps):
+        if t == warmup:
+            t0 = time.perf_counter()
+        o = orc.step(O.synth_image(cfg, 0, t, 0), O.synth_image(cfg, 0, t, 1), ids)
+        if t >= warmup:
+            exits.append(o.exit_layer)
+    dt = time.perf_counter() - t0
+    return {"value": steps / dt, "ms_per_step": 1e3 * dt / steps, "cores": torch.get_num_threads(), "exits": exits,
+            "sample": f"{steps} consecutive batch-1 action-steps of one episode ({desc}, S={S}, fp32 eager, "
+                      f"carried LSTM state, golden thresholds), {warmup} warm-up"}
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    max_layer, exit_ratio, desc = WORKLOADS[a.workload]
+    r = run_cpu_reference(a.workload, a.steps, a.warmup, a.seq)
+    line = {"impl": "reference", "metric": "action-steps/sec", "value": r["value"], "unit": "action-steps/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "batch_per_step": 1, "seq_len": a.seq, "max_layer": max_layer, "exit_ratio": exit_ratio,
+                       "note": "reference CPU path = oracle port of the PyTorch eager forward (the reference is Python; "
+                               "un-vendored ViT/MPT blocks restated), one host process, all host threads"},
+            "cpu_baseline": {"value": r["value"], "unit": "action-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "action-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "exit_layers": r["exits"]}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# engine arm
+# ---------------------------------------------------------------------------------------------------
+def engine_arm(a):
+    import torch.distributed as dist
+    from deer_vla_b200 import config_3b
+    from deer_vla_b200.engine import DeerEngine
+    from deer_vla_b200.value_net import ExitController
+    from deer_vla_b200.weights import synth_frames, synth_instruction_ids, synth_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    max_layer, exit_ratio, desc = WORKLOADS[a.workload]
+    cfg = config_3b(max_layer)
+    B, S = a.batch, a.seq
+    eng = DeerEngine(cfg, max_batch=B, max_slots=B, max_seq=S, device=local, precision="bf16", gemm_impl="tcgen05")
+    t0 = time.time()
+    eng.load_state_dict(synth_state_dict(cfg, 0))
+    t_load = time.time() - t0
+
+    # synthetic inputs: NF distinct frame sets per camera (each step's input set is 2*B*3*224*224*4 B = 270 MB at B=224,
+    # larger than the 126 MB L2, and consecutive steps use different sets) ; episodes sharded by rank (eval_utils.py:523-527)
+    NF = 4
+    frames = [(synth_frames(cfg, B, 1000 + 17 * (rank * NF + i), dev), synth_frames(cfg, B, 5000 + 17 * (rank * NF + i), dev)) for i in range(NF)]
+    ids = synth_instruction_ids(cfg, B, S, seed=2000 + rank).to(dev)
+    mask = torch.ones(B, S, dtype=torch.uint8, device=dev)
+    slots = torch.arange(B, dtype=torch.int32, device=dev)
+
+    # thresholds: GPU calibration (full-depth delta table) + the reference's greedy solver (value_net.py:203-264)
+    ctrl = ExitController(None, exit_id_list=eng.exit_list, steps_per_stage=1, exit_dist="exp", leq=True, max_layer=max_layer, engine=eng)
+    eng.reset()
+    cols = []
+    for t in range(a.calib_steps):
+        r, g = frames[t % NF]
+        out = eng.step(r, g, ids, mask, slots, full_depth=True)
+        cols.append(out["delta"].float().t().cpu())
+    table = torch.cat(cols, dim=1)
+    if world > 1:                                  # the reference all_gathers the per-rank tables (value_net.py:195-201)
+        tl = [torch.zeros_like(table).to(dev) for _ in range(world)]
+        dist.all_gather(tl, table.to(dev))
+        table = torch.cat([x.cpu() for x in tl], dim=1)
+    ctrl.set_threshold(None, None, None, exit_ratio, cfg.llm_name, values=table)
+    thresholds = [ctrl.thresholds[e] for e in ctrl._real_exits()]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed region ------------------------------------------------------------------
+    eng.reset()
+    for t in range(a.warmup):
+        r, g = frames[t % NF]
+        eng.step(r, g, ids, mask, slots, want_delta=False)
+    barrier()
+    launches0 = eng.stats().kernel_launches_total
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    exit_hist = np.zeros(cfg.n_layers, dtype=np.int64)
+    outs = []
+    e0.record()
+    for t in range(a.steps):
+        r, g = frames[(a.warmup + t) % NF]
+        outs.append(eng.step(r, g, ids, mask, slots, want_delta=False))
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.stats().kernel_launches_total - launches0
+    for o in outs:
+        ex = o["exit_layer"].cpu().numpy()
+        exit_hist += np.bincount(ex, minlength=cfg.n_layers)
+    tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_max = float(tt.item())
+    value = world * B * a.steps / (ms_max / 1e3)
+
+    # ---- end-to-end through the public API with host buffers ------------------------------------
+    h_frames = [(r.cpu().pin_memory(), g.cpu().pin_memory()) for r, g in frames[:2]]
+    h_ids, h_mask, h_slots = ids.cpu().pin_memory(), mask.cpu().pin_memory(), slots.cpu().pin_memory()
+    eng.reset()
+    for t in range(2):
+        eng.step(h_frames[t % 2][0], h_frames[t % 2][1], h_ids, h_mask, h_slots, want_delta=False)
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(a.steps):
+        o = eng.step(h_frames[t % 2][0], h_frames[t % 2][1], h_ids, h_mask, h_slots, want_delta=False)
+        _ = float(o["action"][0, 0])                  # host read of the step's result
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * a.steps / float(tt.item())
+    img_bytes = B * 3 * cfg.image_size * cfg.image_size * 4
+    h2d = 2 * img_bytes + B * S * 8 + B * S + B * 4
+    d2h = B * (6 + 1 + 7 + 1) * 4
+
+    # ---- per-kernel profile pass: CUDA events around every GEMM launch on the launching stream ---------
+    eng.set_profile(True)
+    eng.reset()
+    prof_acc = None
+    for t in range(3):
+        r, g = frames[t % NF]
+        eng.step(r, g, ids, mask, slots, want_delta=False)
+        p = eng.profile()
+        if t == 0:
+            continue                                   # first profiled step creates the events
+        if prof_acc is None:
+            prof_acc = {"gemm_ms": dict.fromkeys(p["gemm_ms"], 0.0), "gemm_flops": dict.fromkeys(p["gemm_ms"], 0.0),
+                        "gemm_launches": dict.fromkeys(p["gemm_ms"], 0), "step_ms": 0.0, "n": 0}
+        for k in p["gemm_ms"]:
+            prof_acc["gemm_ms"][k] += p["gemm_ms"][k]
+            prof_acc["gemm_flops"][k] += p["gemm_flops"][k]
+            prof_acc["gemm_launches"][k] += p["gemm_launches"][k]
+        prof_acc["step_ms"] += p["step_ms"]
+        prof_acc["n"] += 1
+        prof_acc["active_after"] = p["active_after"]
+    eng.set_profile(False)
+    peak_tf, peak_bw, peak_src = measured_peaks()
+    g_ms = sum(prof_acc["gemm_ms"].values())
+    g_fl = sum(prof_acc["gemm_flops"].values())
+    g_n = sum(prof_acc["gemm_launches"].values())
+    achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    stages = {k: {"ms_per_step": prof_acc["gemm_ms"][k] / prof_acc["n"],
+                  "tflops": (prof_acc["gemm_flops"][k] / (prof_acc["gemm_ms"][k] * 1e-3) / 1e12) if prof_acc["gemm_ms"][k] > 0 else 0.0,
+                  "launches_per_step": prof_acc["gemm_launches"][k] // prof_acc["n"]} for k in prof_acc["gemm_ms"]}
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<BN> (tcgen05.mma + TMA, all GEMM launches of a step)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "peak_source": peak_src, "algorithmic_flops_per_launch": g_fl / max(1, g_n),
+                "avg_launch_ms": g_ms / max(1, g_n), "gemm_share_of_step": g_ms / prof_acc["step_ms"] if prof_acc["step_ms"] else None,
+                "stages": stages, "active_after_each_exit": prof_acc.get("active_after")}
+
+    # whole-step algorithmic FLOP rate from the measured exit histogram (SURVEY §8d formula)
+    exits_sorted = [e for e in cfg.exit_list if e <= cfg.ctrl_max_layer]
+    total_gflop = sum(int(exit_hist[e]) * algorithmic_gflop_per_step(e, exits_sorted.index(e)) for e in exits_sorted)
+    total_steps = int(exit_hist.sum())
+    step_tflops = (total_gflop / 1e3) / (ms / 1e3) if ms > 0 else 0.0
+
+    # ---- the one collective: gather of the final actions / exit ids to rank 0 (eval_utils.py:565-568) --------
+    last = outs[-1]
+    payload = torch.cat([last["action"], last["exit_layer"].float().unsqueeze(1)], dim=1).contiguous()
+    if world > 1:
+        gl = [torch.zeros_like(payload) for _ in range(world)] if rank == 0 else None
+        dist.gather(payload, gl, dst=0)
+        gathered = torch.cat(gl) if rank == 0 else None
+    else:
+        gathered = payload
+    cpu_base = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        eng.close()
+        torch.cuda.empty_cache()
+        r = run_cpu_reference(a.workload, a.cpu_steps, 1, S)
+        cpu_base = {"value": r["value"], "unit": "action-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    if rank == 0:
+        line = {"metric": "action-steps/sec", "value": value, "unit": "action-steps/s", "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": desc, "episodes_per_gpu": B, "seq_len": S, "max_layer": max_layer, "exit_ratio": exit_ratio,
+                           "parallelism": f"episode-sharded replicas x{world}", "thresholds": thresholds,
+                           "l2": "each step reads a different 270 MB frame set (> 126 MB L2); weights 3.1 GB",
+                           "weights": "seeded synthetic (no checkpoints offline)", "calibration_samples": int(table.shape[1])},
+                "e2e": {"value": e2e_value, "unit": "action-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
+                "exit_histogram": {str(e): int(exit_hist[e]) for e in exits_sorted},
+                "mean_exit_depth_layers": float(sum((e + 1) * exit_hist[e] for e in exits_sorted) / max(1, total_steps)),
+                "step_algorithmic_tflops": step_tflops, "weights_load_s": t_load,
+                "gathered_rows": int(gathered.shape[0])}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="deer_b", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=224, help="concurrent episodes per GPU")
+    ap.add_argument("--seq", type=int, default=32)
+    ap.add_argument("--calib-steps", type=int, default=8)
+    ap.add_argument("--cpu-steps", type=int, default=8, help="batch-1 oracle steps timed for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        if a.warmup < 3:
+            a.warmup = 3
+        engine_arm(a)
+
+
+if __name__ == "__main__":
+    main()

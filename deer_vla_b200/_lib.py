@@ -36,6 +36,11 @@ class DeerStats(C.Structure):
                 ("steps", C.c_int64), ("weight_bytes", C.c_int64), ("workspace_bytes", C.c_int64)]
 
 
+class DeerProfile(C.Structure):
+    _fields_ = [("gemm_ms", C.c_double * 4), ("gemm_flops", C.c_double * 4), ("gemm_launches", C.c_int64 * 4),
+                ("step_ms", C.c_double), ("n_probes", C.c_int32), ("active_after", C.c_int32 * 16)]
+
+
 # every symbol include/deer_engine.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -59,6 +64,8 @@ SYMBOLS = {
     "deer_get_state": (C.c_int, [_P, C.c_int, _P, _P]),
     "deer_get_tap": (C.c_int, [_P, C.c_char_p, C.c_int, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "deer_get_stats": (C.c_int, [_P, C.POINTER(DeerStats)]),
+    "deer_set_profile": (C.c_int, [_P, C.c_int]),
+    "deer_get_profile": (C.c_int, [_P, C.POINTER(DeerProfile)]),
     "deer_op_gemm": (C.c_int, [C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                                _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P]),
     "deer_op_attention": (C.c_int, [C.c_int, C.c_int, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int,

@@ -71,11 +71,21 @@ struct LaunchStats {
 // ---------------------------------------------------------------------------------------------
 // GEMM dispatch (shared by the engine and deer_op_gemm)
 // ---------------------------------------------------------------------------------------------
+struct GemmRec { cudaEvent_t e0, e1; int tag, epoch, m_host, m_mul, n, k; bool dyn; };
 struct GemmCtx {
   std::map<TmapKey, CUtensorMap> tmaps;
   bool attr_set[3] = {false, false, false};
   LaunchStats* stats = nullptr;
   std::string* err = nullptr;
+  // profiling
+  bool profile = false;
+  int tag = 0, epoch = 0;
+  std::vector<GemmRec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get_event() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
 };
 
 template <int BN>
@@ -98,6 +108,11 @@ static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int
                     const GemmEpi& epi, const int* m_dev, int m_mul, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return DEER_OK;
   cudaError_t e;
+  GemmRec rec{};
+  if (g.profile) {
+    rec = GemmRec{g.get_event(), g.get_event(), g.tag, g.epoch, M, m_mul, N, K, m_dev != nullptr};
+    cudaEventRecord(rec.e0, st);
+  }
   if (dtype == 1 || impl == DEER_GEMM_SIMT) {
     dim3 grid((N + 63) / 64, (M + 63) / 64);
     if (dtype == 1)
@@ -131,6 +146,7 @@ static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int
     else if (BN == 128) e = launch_tc<128>(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st, 1);
     else e = launch_tc<64>(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st, 2);
   }
+  if (g.profile) { cudaEventRecord(rec.e1, st); g.recs.push_back(rec); }
   if (e != cudaSuccess) return set_err(g.err, DEER_E_CUDA, "GEMM launch failed: %s", cudaGetErrorString(e));
   if (g.stats) {
     g.stats->total++; g.stats->step++; g.stats->gemm_step++;
@@ -219,6 +235,9 @@ struct deer_ctx {
   float *tap_vit = nullptr, *tap_media = nullptr, *tap_hidden = nullptr, *tap_pooled = nullptr;
   int tap_n = 0, tap_S = 0;
   cudaStream_t own_stream = nullptr;
+  int* nact_hist = nullptr;            // device [16]: active count after each probe of the last step
+  int n_probes_last = 0, n_last = 0;
+  cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
   GemmCtx gemm;
   LaunchStats stats;
   int64_t steps = 0;
@@ -436,6 +455,7 @@ extern "C" int deer_create(const deer_config* cfg, int device, deer_ctx** out) {
   WS(c->s_grip, B * 3 * f.image_size * f.image_size * 4);
   WS(c->s_ids, B * S * 8); WS(c->s_mask, B * S); WS(c->s_slots, B * 4); WS(c->s_ts, B * 4);
   WS(c->thr_dev, std::max(1, c->n_thr) * 4);
+  WS(c->nact_hist, 16 * 4);
   WS(c->alibi, f.n_heads * 4);
   if (f.debug_taps) {
     WS(c->tap_vit, NI * np * Wd * 4);
@@ -475,6 +495,10 @@ extern "C" void deer_destroy(deer_ctx* c) {
   for (auto& kv : c->staged) if (kv.second.dev) cudaFree(kv.second.dev);
   for (void* p : c->allocs) cudaFree(p);
   if (c->h_nact) cudaFreeHost(c->h_nact);
+  for (auto& r : c->gemm.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (auto e : c->gemm.pool) cudaEventDestroy(e);
+  if (c->ev_step0) cudaEventDestroy(c->ev_step0);
+  if (c->ev_step1) cudaEventDestroy(c->ev_step1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -850,6 +874,7 @@ template <typename T> struct StepImpl {
 
   // ---- DeterministicDecoder single-step forward on x (action_head.py:499-611) -> cur_pose / cur_grip / candidate (h,c)
   int head_eval() {
+    struct TagGuard { GemmCtx& g; int old; TagGuard(GemmCtx& g_) : g(g_), old(g_.tag) { g.tag = 3; } ~TagGuard() { g.tag = old; } } tg(c->gemm);
     const deer_config& f = c->cfg;
     const int D = f.d_model, H = f.lstm_hidden, LL = f.lstm_layers, Bm = f.max_batch, d0 = f.mlp_dim0, d1 = f.mlp_dim1;
     const int* nd = nact();
@@ -896,7 +921,17 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
   init_episodes_kernel<<<(n + 127) / 128, 128, 0, st>>>(c->meta[0], c->n_active, slots, ids, mask, timesteps, n, S, f.media_token_id,
                                                           f.steps_per_stage, c->n_thr, exit_out, delta_out);
   KLAUNCH_CHECK("init_episodes");
+  c->n_probes_last = 0; c->n_last = n;
+  c->gemm.epoch = 0;
+  if (c->gemm.profile) {
+    for (auto& r : c->gemm.recs) { c->gemm.pool.push_back(r.e0); c->gemm.pool.push_back(r.e1); }
+    c->gemm.recs.clear();
+    if (!c->ev_step0) { cudaEventCreate(&c->ev_step0); cudaEventCreate(&c->ev_step1); }
+    cudaEventRecord(c->ev_step0, st);
+  }
+  c->gemm.tag = 0;
   RET(s.vision(rgb, grip));
+  c->gemm.tag = 2;
   if (c->dtype == 1) embed_kernel<float><<<n * S, 256, 0, st>>>(ids, reinterpret_cast<const float*>(c->wte), c->x[0], n * S, f.d_model, f.vocab);
   else embed_kernel<bf16><<<n * S, 256, 0, st>>>(ids, reinterpret_cast<const bf16*>(c->wte), c->x[0], n * S, f.d_model, f.vocab);
   KLAUNCH_CHECK("embed");
@@ -929,8 +964,11 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
     g.pose_out = pose_out; g.grip_out = grip_out; g.action_out = action_out; g.exit_out = exit_out; g.delta_out = delta_out;
     g.exit_flag = c->exit_flag; g.src_of_new = c->src_of_new;
     const int nxt = s.cur ^ 1;
-    exit_gate_kernel<<<1, 1024, 0, st>>>(g, c->meta[s.cur], c->n_active + s.cur, c->n_active + nxt);
+    exit_gate_kernel<<<1, 1024, 0, st>>>(g, c->meta[s.cur], c->n_active + s.cur, c->n_active + nxt,
+                                         c->nact_hist + std::min(c->n_probes_last, 15));
     KLAUNCH_CHECK("exit_gate");
+    c->n_probes_last++;
+    c->gemm.epoch = c->n_probes_last;
     commit_state_kernel<<<dim3(n, f.lstm_layers), 256, 0, st>>>(c->exit_flag, c->meta[s.cur].slot, c->cand_h, c->cand_c, c->h_state, c->c_state,
                                                                f.lstm_layers, f.lstm_hidden, f.max_batch, n, c->n_active + s.cur);
     KLAUNCH_CHECK("commit_state");
@@ -947,6 +985,7 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
       s.n = *c->h_nact;                       // exact-sized launches from here on
     }
   }
+  if (c->gemm.profile) cudaEventRecord(c->ev_step1, st);
   return DEER_OK;
 }
 
@@ -1039,6 +1078,40 @@ extern "C" int deer_get_tap(deer_ctx* c, const char* name, int layer, float* out
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out, src, numel * 4, cudaMemcpyDeviceToHost));
   for (int i = 0; i < 4; ++i) shape_out[i] = sh[i];
+  return DEER_OK;
+}
+
+extern "C" int deer_set_profile(deer_ctx* c, int enable) {
+  if (!c) return set_err(nullptr, DEER_E_INVALID, "null ctx");
+  c->gemm.profile = enable != 0;
+  return DEER_OK;
+}
+
+extern "C" int deer_get_profile(deer_ctx* c, deer_profile* out) {
+  if (!c || !out) return set_err(c ? &c->err : nullptr, DEER_E_INVALID, "null argument");
+  cudaSetDevice(c->device);
+  CK(cudaDeviceSynchronize());
+  memset(out, 0, sizeof(*out));
+  int hist[16] = {0};
+  CK(cudaMemcpy(hist, c->nact_hist, sizeof(hist), cudaMemcpyDeviceToHost));
+  out->n_probes = c->n_probes_last;
+  for (int i = 0; i < 16; ++i) out->active_after[i] = (i < c->n_probes_last) ? hist[i] : 0;
+  for (const GemmRec& r : c->gemm.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+    int M = r.m_host;
+    if (r.dyn) {
+      const int act = (r.epoch == 0) ? c->n_last : hist[std::min(r.epoch - 1, 15)];
+      M = std::min(M, act * r.m_mul);
+    }
+    out->gemm_ms[r.tag] += ms;
+    out->gemm_flops[r.tag] += 2.0 * M * r.n * r.k;
+    out->gemm_launches[r.tag]++;
+  }
+  if (c->ev_step0 && c->gemm.profile) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev_step0, c->ev_step1) == cudaSuccess) out->step_ms = ms;
+  }
   return DEER_OK;
 }
 

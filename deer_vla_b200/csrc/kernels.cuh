@@ -321,7 +321,7 @@ struct GateParams {
 };
 
 __global__ void __launch_bounds__(1024)
-exit_gate_kernel(GateParams g, EpisodeMeta m, const int* __restrict__ n_cur, int* __restrict__ n_next) {
+exit_gate_kernel(GateParams g, EpisodeMeta m, const int* __restrict__ n_cur, int* __restrict__ n_next, int* __restrict__ hist) {
   __shared__ int wsum[32];
   __shared__ int total;
   const int n = *n_cur;
@@ -398,7 +398,7 @@ exit_gate_kernel(GateParams g, EpisodeMeta m, const int* __restrict__ n_cur, int
   __syncthreads();
   const int pos = wsum[warp] + incl - survive;
   if (survive) g.src_of_new[pos] = r;
-  if (threadIdx.x == 0) *n_next = total;
+  if (threadIdx.x == 0) { *n_next = total; *hist = total; }
 }
 
 // commit the candidate LSTM state of the episodes that exit now (update_hidden_state=True, action_head.py:554-556)

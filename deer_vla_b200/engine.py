@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import DeerCConfig, DeerError, DeerStats
+from ._lib import DeerCConfig, DeerError, DeerProfile, DeerStats
 from .config import DeerConfig
 
 
@@ -98,6 +98,19 @@ class DeerEngine:
         s = DeerStats()
         self._check(self.lib.deer_get_stats(self._h, C.byref(s)))
         return s
+
+    def set_profile(self, enable: bool):
+        self._check(self.lib.deer_set_profile(self._h, int(enable)))
+
+    def profile(self) -> dict:
+        """Per-stage GEMM device time / exact algorithmic FLOPs of the last step (synchronises)."""
+        p = DeerProfile()
+        self._check(self.lib.deer_get_profile(self._h, C.byref(p)))
+        stages = ("vit", "perceiver", "llm", "head")
+        return {"gemm_ms": {s: p.gemm_ms[i] for i, s in enumerate(stages)},
+                "gemm_flops": {s: p.gemm_flops[i] for i, s in enumerate(stages)},
+                "gemm_launches": {s: int(p.gemm_launches[i]) for i, s in enumerate(stages)},
+                "step_ms": p.step_ms, "active_after": [int(p.active_after[i]) for i in range(p.n_probes)]}
 
     # ---- weights ----------------------------------------------------------------------------
     def load_state_dict(self, sd: Mapping[str, "torch.Tensor | np.ndarray"], strict: bool = True):

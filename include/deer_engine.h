@@ -151,6 +151,21 @@ int deer_step_host(deer_ctx* ctx, int n, const int32_t* slots, const float* rgb,
                    int static_exit, uint32_t flags,
                    float* pose_out, float* gripper_out, float* action_out, int32_t* exit_out, float* delta_out);
 
+/* measurement: with profiling on, every GEMM launch of the following steps is bracketed by CUDA events on the
+ * launching stream, and the device-side active-episode count after every exit is recorded, so the exact
+ * algorithmic FLOPs (2*M_actual*N*K) and the device time of the dominant kernel are known per stage.
+ * stage index: 0 ViT, 1 Perceiver, 2 LLM (x-attn + MPT), 3 action head.  deer_get_profile synchronises. */
+typedef struct deer_profile {
+  double  gemm_ms[4];
+  double  gemm_flops[4];
+  int64_t gemm_launches[4];
+  double  step_ms;            /* device time of the whole last step (first to last kernel) */
+  int32_t n_probes;           /* exits evaluated in the last step */
+  int32_t active_after[16];   /* still-active episodes after each probe */
+} deer_profile;
+int deer_set_profile(deer_ctx* ctx, int enable);
+int deer_get_profile(deer_ctx* ctx, deer_profile* out);
+
 /* introspection for parity tests (the reference exposes .hidden_states / module attributes) */
 int deer_get_state(deer_ctx* ctx, int slot, float* h_out, float* c_out);   /* HOST [layers, hidden] each */
 /* name: "vit" [2n, patches, width] (rgb images then gripper images), "media" [n, 2*latents, width],
