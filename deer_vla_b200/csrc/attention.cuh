@@ -89,6 +89,82 @@ attn_simt_kernel(AttnParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// attn_small_kernel<T>: the LLM-side attentions (gated x-attn S x 128 latents, MPT self-attention S x S,
+// S <= 32).  One CTA (256 threads) per (batch, head): Q, K, V staged ONCE in shared memory as fp32
+// (rows padded to hd+1 floats -> conflict-free), scores + softmax + PV entirely on chip.  Same masks /
+// bias semantics as attn_simt_kernel.  The FLOPs are negligible; what matters is that K/V are read from
+// HBM/L2 once per (b,h) instead of once per query row.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+attn_small_kernel(AttnParams p) {
+  extern __shared__ float sm[];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int nb = p.n_dev ? min(*p.n_dev, p.B_host) : p.B_host;
+  if (b >= nb) return;
+  const int hd = p.hd, hp = hd + 1, Sq = p.Sq, Sk = p.Sk, skp = Sk + 1;
+  float* sq = sm;                         // [Sq][hp]
+  float* sk = sq + Sq * hp;               // [Sk][hp]
+  float* sv = sk + Sk * hp;               // [Sk][hp]
+  float* ss = sv + Sk * hp;               // [Sq][skp]
+  const T* Q = reinterpret_cast<const T*>(p.Q) + static_cast<size_t>(b) * Sq * p.ldq + h * hd;
+  const T* K = reinterpret_cast<const T*>(p.K) + static_cast<size_t>(b) * Sk * p.ldk + h * hd;
+  const T* V = reinterpret_cast<const T*>(p.V) + static_cast<size_t>(b) * Sk * p.ldv + h * hd;
+  T* O = reinterpret_cast<T*>(p.O) + static_cast<size_t>(b) * Sq * p.ldo + h * hd;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < Sq * hd; idx += 256) { const int i = idx / hd, d = idx % hd; sq[i * hp + d] = to_f32<T>(Q[static_cast<size_t>(i) * p.ldq + d]); }
+  for (int idx = tid; idx < Sk * hd; idx += 256) {
+    const int j = idx / hd, d = idx % hd;
+    sk[j * hp + d] = to_f32<T>(K[static_cast<size_t>(j) * p.ldk + d]);
+    sv[j * hp + d] = to_f32<T>(V[static_cast<size_t>(j) * p.ldv + d]);
+  }
+  __syncthreads();
+  const int kvl = p.kv_len ? p.kv_len[b] : Sk;
+  const float slope = p.alibi_slopes ? p.alibi_slopes[h] : 0.0f;
+  for (int idx = tid; idx < Sq * Sk; idx += 256) {
+    const int i = idx / Sk, j = idx % Sk;          // consecutive threads -> consecutive keys (distinct smem rows)
+    const int mode = p.qmode ? p.qmode[b * Sq + i] : 1;
+    const int jmax = p.causal ? (i + (Sk - Sq)) : (Sk - 1);
+    float acc = 0.0f;
+    const float* qr = sq + i * hp;
+    const float* kr = sk + j * hp;
+#pragma unroll 8
+    for (int d = 0; d < hd; ++d) acc = fmaf(qr[d], kr[d], acc);
+    float s = acc * p.scale + slope * static_cast<float>(j - (Sk - 1));
+    if (mode == 2) s = 0.0f;
+    else if (j > jmax || j >= kvl) s = -INFINITY;
+    ss[i * skp + j] = s;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int i = warp; i < Sq; i += 8) {
+    float m = -INFINITY;
+    for (int j = lane; j < Sk; j += 32) m = fmaxf(m, ss[i * skp + j]);
+    m = warp_max(m);
+    float l = 0.0f;
+    for (int j = lane; j < Sk; j += 32) {
+      const float v = ss[i * skp + j];
+      const float e = (v == -INFINITY) ? 0.0f : expf(v - m);
+      ss[i * skp + j] = e;
+      l += e;
+    }
+    l = warp_sum(l);
+    const int mode = p.qmode ? p.qmode[b * Sq + i] : 1;
+    const float inv = (mode == 0) ? 0.0f : 1.0f / l;     // mode 0: attention zeroed (helpers.py:223-229)
+    for (int j = lane; j < Sk; j += 32) ss[i * skp + j] *= inv;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < Sq * hd; idx += 256) {
+    const int i = idx / hd, d = idx % hd;              // consecutive threads -> consecutive d (conflict-free V reads)
+    float acc = 0.0f;
+    const float* pr = ss + i * skp;
+    for (int j = 0; j < Sk; ++j) acc = fmaf(pr[j], sv[j * hp + d], acc);
+    O[static_cast<size_t>(i) * p.ldo + d] = from_f32<T>(acc);
+  }
+}
+static inline size_t attn_small_smem(int Sq, int Sk, int hd) { return (static_cast<size_t>(Sq + 2 * Sk) * (hd + 1) + static_cast<size_t>(Sq) * (Sk + 1)) * sizeof(float); }
+
+// ---------------------------------------------------------------------------------------------
 // flash attention, bf16, head_dim 64, no mask.  grid (ceil(Sq/64), H, B), 128 threads.
 // Each warp owns 16 query rows; K/V streamed in 64-key tiles through double-buffered smem.
 // ---------------------------------------------------------------------------------------------
@@ -173,24 +249,31 @@ flash_attn_hd64_kernel(const bf16* __restrict__ Qg, int ldq, const bf16* __restr
         ldsm_x4(qa[kk], sQ + swz(r, c));
       }
     }
+    const int kbase = t * 64;
+    const int kvalid = min(64, Sk - kbase);                 // valid keys in this tile
+    const int np_valid = (kvalid + 15) >> 4;                // 16-key groups that contain a valid key
+    const bool warp_active = (q0 + warp * 16) < Sq;         // warps whose 16 query rows are all padding skip the math
     // S = Q K^T  (16 x 64 per warp)
     float s[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.0f; }
+    if (warp_active) {
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
-        uint32_t kb[4];
-        const int r = np * 16 + (lane & 7) + (lane >> 4) * 8;
-        const int c = kk * 16 + ((lane >> 3) & 1) * 8;
-        ldsm_x4(kb, sK[buf] + swz(r, c));
-        mma_bf16_16816(s[2 * np], qa[kk], kb[0], kb[1]);
-        mma_bf16_16816(s[2 * np + 1], qa[kk], kb[2], kb[3]);
+        if (np < np_valid) {
+          uint32_t kb[4];
+          const int r = np * 16 + (lane & 7) + (lane >> 4) * 8;
+          const int c = kk * 16 + ((lane >> 3) & 1) * 8;
+          ldsm_x4(kb, sK[buf] + swz(r, c));
+          mma_bf16_16816(s[2 * np], qa[kk], kb[0], kb[1]);
+          mma_bf16_16816(s[2 * np + 1], qa[kk], kb[2], kb[3]);
+        }
       }
     }
+    }
     // online softmax (log2 domain)
-    const int kbase = t * 64;
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
@@ -224,9 +307,11 @@ flash_attn_hd64_kernel(const bf16* __restrict__ Qg, int ldq, const bf16* __restr
     l0 = l0 * a0 + rs0; l1 = l1 * a1 + rs1;
 #pragma unroll
     for (int n = 0; n < 8; ++n) { o[n][0] *= a0; o[n][1] *= a0; o[n][2] *= a1; o[n][3] *= a1; }
-    // O += P V
+    // O += P V   (16-key groups past the last valid key contribute p = 0: skipped)
+    if (warp_active) {
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
+      if (kk >= np_valid) break;
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
         uint32_t vb[4];
@@ -236,6 +321,7 @@ flash_attn_hd64_kernel(const bf16* __restrict__ Qg, int ldq, const bf16* __restr
         mma_bf16_16816(o[2 * np], pa[kk], vb[0], vb[1]);
         mma_bf16_16816(o[2 * np + 1], pa[kk], vb[2], vb[3]);
       }
+    }
     }
     __syncthreads();
   }

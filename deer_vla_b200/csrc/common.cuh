@@ -38,6 +38,25 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.0f);
   return v;
 }
+// Fast forms for the tensor-core epilogue (results are rounded to bf16 or added to an O(1) fp32 residual):
+// erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7) with __expf / fast reciprocal; QuickGELU with fast divide.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-z * z);           // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
+__device__ __forceinline__ float quick_gelu_fast(float x) { return __fdividef(x, 1.0f + __expf(fminf(-1.702f * x, 80.0f))); }
+__device__ __forceinline__ float apply_act_fast(float v, int act) {
+  if (act == ACT_GELU) return gelu_erf_fast(v);
+  if (act == ACT_QUICKGELU) return quick_gelu_fast(v);
+  if (act == ACT_RELU) return fmaxf(v, 0.0f);
+  return v;
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // ---- warp / block reductions ---------------------------------------------------------------

@@ -162,6 +162,17 @@ static int run_attention(int impl, int dtype, const AttnParams& p, std::string* 
     flash_attn_hd64_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const bf16*>(p.Q), p.ldq, reinterpret_cast<const bf16*>(p.K),
                                                  reinterpret_cast<const bf16*>(p.V), p.ldk, reinterpret_cast<bf16*>(p.O), p.ldo, p.Sq, p.Sk,
                                                  p.scale * 1.4426950408889634f);
+  } else if (impl == 2 && attn_small_smem(p.Sq, p.Sk, p.hd) <= 200 * 1024) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(attn_small_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(attn_small_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_done = true;
+    }
+    dim3 grid(p.H, p.B_host);
+    const size_t sm = attn_small_smem(p.Sq, p.Sk, p.hd);
+    if (dtype == 1) attn_small_kernel<float><<<grid, 256, sm, st>>>(p);
+    else attn_small_kernel<bf16><<<grid, 256, sm, st>>>(p);
   } else {
     dim3 grid(p.Sq, p.H, p.B_host);
     const size_t sm = (p.hd + p.Sk + 8) * sizeof(float);
@@ -759,8 +770,21 @@ template <typename T> struct StepImpl {
   int ln(const TIn* in, int in_ld, const float* g, const float* b, int groups, int D, TOut* out, int out_ld, LnMap map, TOut* out2, int out2_ld,
          int relu, int rows, const int* n_dev, int n_mul, LnMap in_map = LnMap{0, 0, 0}) {
     if (rows <= 0) return DEER_OK;
-    const int grid = std::min(rows, DEER_NUM_SMS * 16);
-    layernorm_kernel<TIn, TOut><<<grid, 128, 0, st>>>(in, in_ld, in_map, g, b, groups, D, out, out_ld, map, out2, out2_ld, relu, rows, n_dev, n_mul);
+    const bool vec_ok = (D % 128 == 0) && (in_ld % 4 == 0) && (out_ld % 4 == 0) && (out2 == nullptr || out2_ld % 4 == 0);
+    const int nvec = D / 128;
+    const int wgrid = (rows + 3) / 4;
+#define LNW(NV) layernorm_warp_kernel<TIn, TOut, NV><<<wgrid, 128, 0, st>>>(in, in_ld, in_map, g, b, groups, out, out_ld, map, out2, out2_ld, relu, rows, n_dev, n_mul)
+    if (vec_ok && nvec == 1) LNW(1);
+    else if (vec_ok && nvec == 2) LNW(2);
+    else if (vec_ok && nvec == 4) LNW(4);
+    else if (vec_ok && nvec == 8) LNW(8);
+    else if (vec_ok && nvec == 16) LNW(16);
+    else if (vec_ok && nvec == 32) LNW(32);
+    else {
+      const int grid = std::min(rows, DEER_NUM_SMS * 16);
+      layernorm_kernel<TIn, TOut><<<grid, 128, 0, st>>>(in, in_ld, in_map, g, b, groups, D, out, out_ld, map, out2, out2_ld, relu, rows, n_dev, n_mul);
+    }
+#undef LNW
     KLAUNCH_CHECK("layernorm");
     return DEER_OK;
   }
@@ -841,7 +865,7 @@ template <typename T> struct StepImpl {
       a.Q = c->l_q; a.K = c->l_kv; a.V = tp(c->l_kv) + xin; a.O = c->l_att;
       a.ldq = xin; a.ldk = a.ldv = 2 * xin; a.ldo = xin; a.Sq = S; a.Sk = nl2; a.H = f.xattn_heads; a.hd = 64; a.scale = 0.125f;
       a.qmode = c->meta[cur].xmode; a.B_host = n; a.n_dev = nd;
-      RET(run_attention(1, c->dtype, a, &c->err, &c->stats, st));
+      RET(run_attention(2, c->dtype, a, &c->err, &c->stats, st));
       RET(gemm(c->l_att, xin, Mmax, w.xw_out, xin, M, D, xin, x, D, 1, nullptr, ACT_NONE, w.attn_gate_tanh, x, D, nd, S));
       RET(ln<float, T>(x, D, w.xff_g, w.xff_b, 1, D, tp(c->l_ln), D, id, nullptr, 0, 0, M, nd, S));
       const int ffd = f.xattn_ff_mult * D;
@@ -859,7 +883,7 @@ template <typename T> struct StepImpl {
     a.Q = c->l_qkv; a.K = tp(c->l_qkv) + D; a.V = tp(c->l_qkv) + 2 * D; a.O = c->l_att;
     a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D; a.Sq = a.Sk = S; a.H = f.n_heads; a.hd = c->hd; a.scale = 1.0f / std::sqrt((float)c->hd);
     a.causal = 1; a.alibi_slopes = c->alibi; a.kv_len = c->meta[cur].valid_len; a.B_host = n; a.n_dev = nd;
-    RET(run_attention(1, c->dtype, a, &c->err, &c->stats, st));
+    RET(run_attention(2, c->dtype, a, &c->err, &c->stats, st));
     RET(gemm(c->l_att, D, Mmax, w.w_out, D, M, D, D, x, D, 1, nullptr, ACT_NONE, nullptr, x, D, nd, S));
     RET(ln<float, T>(x, D, w.ln2_g, nullptr, 1, D, tp(c->l_ln), D, id, nullptr, 0, 0, M, nd, S));
     const int ffd = f.mlp_ratio * D;

@@ -130,7 +130,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
 // ---------------------------------------------------------------------------------------------
 // shared epilogue: one output row, NV consecutive columns starting at col0
 // ---------------------------------------------------------------------------------------------
-template <int NV>
+template <int NV, bool FAST = false>
 __device__ __forceinline__ void epi_store(const GemmEpi& e, float sc, int row, int col0, int N, float (&v)[NV]) {
   const bool full = (col0 + NV <= N);
   if (e.bias != nullptr) {
@@ -140,7 +140,7 @@ __device__ __forceinline__ void epi_store(const GemmEpi& e, float sc, int row, i
   }
   if (e.act != ACT_NONE) {
 #pragma unroll
-    for (int j = 0; j < NV; ++j) v[j] = apply_act(v[j], e.act);
+    for (int j = 0; j < NV; ++j) v[j] = FAST ? apply_act_fast(v[j], e.act) : apply_act(v[j], e.act);
   }
 #pragma unroll
   for (int j = 0; j < NV; ++j) v[j] *= sc;
@@ -201,11 +201,12 @@ struct GemmTc {
   static constexpr int TMEM_COLS = 2 * BN;            // two accumulator buffers (128 / 256 / 512 columns)
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual 1 KiB alignment
-  static constexpr int THREADS = 192;                 // warp0 TMA, warp1 MMA+TMEM alloc, warps2-5 epilogue
+  static constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quarter, each owning half of the columns
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS; // warp0 TMA, warp1 MMA+TMEM alloc, warps2-9 epilogue
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(GemmTc<BN>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M_host, const int* __restrict__ m_dev, int m_mul, int N, int K, GemmEpi epi) {
   using G = GemmTc<BN>;
@@ -235,7 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], G::EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -296,6 +297,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===== epilogue warps: TMEM -> registers -> global =====
     const int lane_grp = warp & 3;                      // TMEM lane quarter this warp may access
+    const int col_half = (warp - 2) >> 2;               // which half of the tile's columns this warp drains
+    constexpr int CH = BN / 64;                         // 32-column chunks per half
     const float sc = (epi.scale != nullptr) ? __ldg(epi.scale) : 1.0f;
     int as = 0;
     uint32_t aph = 0;
@@ -306,12 +309,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row = m_blk * G::BM + lane_grp * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(as * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = col_half * CH; c < (col_half + 1) * CH; ++c) {
         float v[32];
         tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
         tmem_ld_wait();
         const int col0 = n_blk * BN + c * 32;
-        if (row < M && col0 < N) epi_store<32>(epi, sc, row, col0, N, v);
+        if (row < M && col0 < N) epi_store<32, true>(epi, sc, row, col0, N, v);
       }
       tc_fence_before();
       __syncwarp();

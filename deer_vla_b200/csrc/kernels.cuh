@@ -99,6 +99,69 @@ layernorm_kernel(const TIn* in, int in_ld, LnMap in_map, const float* __restrict
   }
 }
 
+// Fast path: one WARP per row, D = NVEC*128, row held in registers as float4s, no block barriers.
+// Same two-pass fp32 statistics and the same row maps as layernorm_kernel (in == out allowed).
+template <typename T> struct Vec4IO;
+template <> struct Vec4IO<float> {
+  static __device__ __forceinline__ float4 ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Vec4IO<bf16> {
+  static __device__ __forceinline__ float4 ld(const bf16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+  }
+  static __device__ __forceinline__ void st(bf16* p, float4 v) {
+    uint2 u; u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+template <typename TIn, typename TOut, int NVEC>
+__global__ void __launch_bounds__(128)
+layernorm_warp_kernel(const TIn* in, int in_ld, LnMap in_map, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      int groups, TOut* out, int out_ld, LnMap map, TOut* out2, int out2_ld,
+                      int relu, int rows_host, const int* __restrict__ n_dev, int n_mul) {
+  constexpr int D = NVEC * 128;
+  const int rows = dyn_rows(rows_host, n_dev, n_mul);
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const TIn* x = in + ln_out_row(r, in_map) * in_ld;
+  float4 v[NVEC];
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    v[i] = Vec4IO<TIn>::ld(x + (lane + 32 * i) * 4);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+  const size_t goff = static_cast<size_t>(groups > 1 ? (r % groups) : 0) * D;
+  TOut* o = out + ln_out_row(r, map) * out_ld;
+  TOut* o2 = out2 ? out2 + static_cast<size_t>(r) * out2_ld : nullptr;
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    const int j = (lane + 32 * i) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + goff + j);
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (beta) b = *reinterpret_cast<const float4*>(beta + goff + j);
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + b.x; y.y = (v[i].y - mean) * rstd * g.y + b.y;
+    y.z = (v[i].z - mean) * rstd * g.z + b.z; y.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+    Vec4IO<TOut>::st(o + j, y);
+    if (o2) Vec4IO<TOut>::st(o2 + j, y);
+  }
+}
+
 // ViT token assembly + ln_pre: x[img, 0] = cls + pos[0]; x[img, 1+p] = patch[img*np+p] + pos[1+p]; x = ln_pre(x)
 template <typename T>
 __global__ void __launch_bounds__(128)
