@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <tuple>
@@ -74,7 +75,7 @@ struct LaunchStats {
 struct GemmRec { cudaEvent_t e0, e1; int tag, epoch, m_host, m_mul, n, k; bool dyn; };
 struct GemmCtx {
   std::map<TmapKey, CUtensorMap> tmaps;
-  bool attr_set[3] = {false, false, false};
+  bool attr_set[4] = {false, false, false, false};
   LaunchStats* stats = nullptr;
   std::string* err = nullptr;
   // profiling
@@ -103,7 +104,21 @@ static cudaError_t launch_tc(GemmCtx& g, const CUtensorMap& ta, const CUtensorMa
   return cudaGetLastError();
 }
 
-// dtype: 0 bf16, 1 fp32.  impl: DEER_GEMM_*.  a_rows: allocated rows of A (>= M) for the TMA bounds.
+static cudaError_t launch_tc2(GemmCtx& g, const CUtensorMap& ta, const CUtensorMap& tb, int M, const int* m_dev, int m_mul, int N, int K,
+                              const GemmEpi& epi, cudaStream_t st) {
+  using G = GemmTc2;
+  if (!g.attr_set[3]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    g.attr_set[3] = true;
+  }
+  const int tiles = ((M + 255) / 256) * ((N + 255) / 256);
+  const int clusters = std::max(1, std::min(tiles, DEER_NUM_SMS / 2));
+  gemm_tc2_kernel<<<2 * clusters, G::THREADS, G::SMEM_BYTES, st>>>(ta, tb, M, m_dev, m_mul, N, K, epi);
+  return cudaGetLastError();
+}
+
+// dtype: 0 bf16, 1 fp32.  impl: DEER_GEMM_* (2 = force the 1-CTA tcgen05 kernel, for A/B comparisons).  a_rows: allocated rows of A (>= M) for the TMA bounds.
 static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int a_rows, const void* W, int ldw, int M, int N, int K,
                     const GemmEpi& epi, const int* m_dev, int m_mul, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return DEER_OK;
@@ -125,7 +140,9 @@ static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int
       return set_err(g.err, DEER_E_INVALID, "tcgen05 GEMM needs 16-byte aligned operands (lda=%d ldw=%d)", lda, ldw);
     const int mt = (M + 127) / 128;
     int BN;
-    if (mt * ((N + 255) / 256) >= 2 * DEER_NUM_SMS && N >= 256) BN = 256;
+    const bool use2 = (impl != 2) && N >= 256 && ((M + 255) / 256) * ((N + 255) / 256) >= DEER_NUM_SMS / 2;
+    if (use2) BN = 128;                       // B box = this CTA's 128-row half of the 256-wide tile
+    else if (mt * ((N + 255) / 256) >= 2 * DEER_NUM_SMS && N >= 256) BN = 256;
     else if (mt * ((N + 127) / 128) >= DEER_NUM_SMS && N >= 128) BN = 128;
     else BN = 64;
     TmapKey ka{A, (uint64_t)a_rows, (uint64_t)K, (uint64_t)lda, 128u};
@@ -142,7 +159,8 @@ static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int
       if (!make_tmap(&tm, W, N, K, ldw, BN)) return set_err(g.err, DEER_E_CUDA, "cuTensorMapEncodeTiled failed for W (%d x %d ld %d)", N, K, ldw);
       ib = g.tmaps.emplace(kb, tm).first;
     }
-    if (BN == 256) e = launch_tc<256>(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st, 0);
+    if (use2) e = launch_tc2(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st);
+    else if (BN == 256) e = launch_tc<256>(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st, 0);
     else if (BN == 128) e = launch_tc<128>(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st, 1);
     else e = launch_tc<64>(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st, 2);
   }
@@ -763,7 +781,7 @@ template <typename T> struct StepImpl {
 
   int gemm(const void* A, int lda, int a_rows, const void* W, int ldw, int M, int N, int K, void* C, int ldc, int out_f32, const float* bias,
            int act, const float* scale, const float* resid, int ldr, const int* m_dev, int m_mul) {
-    GemmEpi e{C, ldc, (c->dtype == 1) ? 1 : out_f32, bias, act, scale, resid, ldr};
+    GemmEpi e{C, ldc, (c->dtype == 1) ? 1 : out_f32, bias, act, scale, resid, ldr, 0};
     return run_gemm(c->gemm, c->cfg.gemm_impl, c->dtype, A, lda, a_rows, W, ldw, M, N, K, e, m_dev, m_mul, st);
   }
   template <typename TIn, typename TOut>
@@ -1162,7 +1180,8 @@ extern "C" int deer_op_gemm(int impl, int dtype, const void* A, int lda, const v
                             void* stream) {
   if (!A || !W || !C) return set_err(nullptr, DEER_E_INVALID, "null pointer");
   g_op_gemm.err = &g_op_err;
-  GemmEpi e{C, ldc, dtype == 1 ? 1 : out_f32, bias, act, scale, resid, ldc};
+  static int dbg = getenv("DEER_EPI_DBG") ? atoi(getenv("DEER_EPI_DBG")) : 0;
+  GemmEpi e{C, ldc, dtype == 1 ? 1 : out_f32, bias, act, scale, resid, ldc, dbg};
   int r = run_gemm(g_op_gemm, impl, dtype, A, lda, M, W, ldw, M, N, K, e, m_dev, m_mul, reinterpret_cast<cudaStream_t>(stream));
   if (g_op_gemm.tmaps.size() > 4096) g_op_gemm.tmaps.clear();
   return r;

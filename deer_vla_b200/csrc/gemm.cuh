@@ -20,6 +20,7 @@ struct GemmEpi {
   const float* scale;  // device scalar (e.g. tanh(attn_gate)) or nullptr
   const float* resid;  // fp32 [M, ldr] or nullptr (may alias C)
   int ldr;
+  int dbg;             // 0 normal; tuning only: 1 = direct (row-per-thread) stores in the 2-CTA kernel, 2 = skip stores
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -130,6 +131,20 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
 // ---------------------------------------------------------------------------------------------
 // shared epilogue: one output row, NV consecutive columns starting at col0
 // ---------------------------------------------------------------------------------------------
+// activation + scale with the (warp-uniform) activation switch hoisted OUT of the element loop
+template <int NV, int ACT>
+__device__ __forceinline__ void epi_act_scale_t(float sc, float (&v)[NV]) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) v[j] = act_fast<ACT>(v[j]) * sc;
+}
+template <int NV>
+__device__ __forceinline__ void epi_act_scale(int act, float sc, float (&v)[NV]) {
+  if (act == ACT_NONE) epi_act_scale_t<NV, ACT_NONE>(sc, v);
+  else if (act == ACT_GELU) epi_act_scale_t<NV, ACT_GELU>(sc, v);
+  else if (act == ACT_QUICKGELU) epi_act_scale_t<NV, ACT_QUICKGELU>(sc, v);
+  else epi_act_scale_t<NV, ACT_RELU>(sc, v);
+}
+
 template <int NV, bool FAST = false>
 __device__ __forceinline__ void epi_store(const GemmEpi& e, float sc, int row, int col0, int N, float (&v)[NV]) {
   const bool full = (col0 + NV <= N);
@@ -138,12 +153,15 @@ __device__ __forceinline__ void epi_store(const GemmEpi& e, float sc, int row, i
     for (int j = 0; j < NV; ++j)
       if (full || col0 + j < N) v[j] += __ldg(e.bias + col0 + j);
   }
-  if (e.act != ACT_NONE) {
+  if (FAST) epi_act_scale<NV>(e.act, sc, v);
+  else {
+    if (e.act != ACT_NONE) {
 #pragma unroll
-    for (int j = 0; j < NV; ++j) v[j] = FAST ? apply_act_fast(v[j], e.act) : apply_act(v[j], e.act);
+      for (int j = 0; j < NV; ++j) v[j] = apply_act(v[j], e.act);
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] *= sc;
   }
-#pragma unroll
-  for (int j = 0; j < NV; ++j) v[j] *= sc;
   if (e.resid != nullptr) {
     const float* rp = e.resid + static_cast<size_t>(row) * e.ldr + col0;
     if (full && (e.ldr & 3) == 0) {
@@ -327,6 +345,282 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, G::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2-CTA tcgen05 GEMM (cta_group::2): a CTA pair (cluster of 2, same TPC) computes a 256 x 256 tile.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 N-rows), so shared-memory
+// fill + operand-read traffic per SM is 2/3 of the 1-CTA kernel's and the L2->SM traffic per FLOP halves
+// for B.  The leader CTA's single MMA thread issues tcgen05.mma.cta_group::2 (M=256,N=256,K=16); the
+// accumulator rows 0-127 land in the leader's TMEM, rows 128-255 in the peer's.  Both CTAs' TMA loads
+// complete_tx on the LEADER's full barrier; tcgen05.commit multicasts the "stage free" / "accumulator
+// ready" arrivals to both CTAs.  Epilogue: TMEM -> registers -> per-warp smem transpose -> fully
+// coalesced global loads/stores (row-contiguous), 8 epilogue warps per CTA.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // relaxed: the consumer only needs this warp's TMEM reads to be done (tcgen05.wait::ld + fence::before_thread_sync);
+  // a release at cluster scope would wait for the tile's global stores to drain (ERRBAR stall in the ncu source view)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorMap* tm, uint32_t leader_bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(leader_bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {     // arrives on `bar` in BOTH CTAs of the pair
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
+// Coalesced epilogue for one 32x32 fp32 accumulator chunk held one-row-per-lane in v[].  The raw accumulators are
+// transposed through this warp's 32x36-float smem buffer; bias / activation / scale / residual are then applied in the
+// ROW-CONTIGUOUS layout (8 lanes cover the 32 columns of a row, a warp instruction covers 4 rows), so every global
+// access is a full 128 B (fp32) or 64 B (bf16) row segment and the bias / residual loads are issued before the
+// TMEM data is needed (nothing on the critical path waits on a dependent global load).
+template <int ACT>
+__device__ __forceinline__ float4 epi_math4(float4 t, float4 b, float sc) {
+  t.x = act_fast<ACT>(t.x + b.x) * sc; t.y = act_fast<ACT>(t.y + b.y) * sc;
+  t.z = act_fast<ACT>(t.z + b.z) * sc; t.w = act_fast<ACT>(t.w + b.w) * sc;
+  return t;
+}
+template <int ACT>
+__device__ __forceinline__ void epi_store_coalesced_t(const GemmEpi& e, float sc, int row0, int col0, int M, int N, float (&v)[32],
+                                                      float* stage, int lane) {
+  const bool fullc = (col0 + 32 <= N);
+  const bool vec_ok = fullc && ((e.ldc & 7) == 0) && (e.resid == nullptr || (e.ldr & 3) == 0);
+  const int sub = lane >> 3, c4 = (lane & 7) * 4;
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 rs[8];
+  if (vec_ok) {
+    if (e.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + c4));
+    if (e.resid != nullptr) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = row0 + it * 4 + sub;
+        rs[it] = (row < M) ? *reinterpret_cast<const float4*>(e.resid + static_cast<size_t>(row) * e.ldr + col0 + c4)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stage + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  __syncwarp();
+  if (vec_ok) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + sub;
+      const int row = row0 + rr;
+      float4 t = epi_math4<ACT>(*reinterpret_cast<const float4*>(stage + rr * 36 + c4), b4, sc);
+      if (row < M) {
+        if (e.resid != nullptr) { t.x += rs[it].x; t.y += rs[it].y; t.z += rs[it].z; t.w += rs[it].w; }
+        if (e.out_f32) {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.C) + static_cast<size_t>(row) * e.ldc + col0 + c4) = t;
+        } else {
+          uint2 o; o.x = pack_bf16x2(t.x, t.y); o.y = pack_bf16x2(t.z, t.w);
+          *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.C) + static_cast<size_t>(row) * e.ldc + col0 + c4) = o;
+        }
+      }
+    }
+  } else {
+    const int col = col0 + lane;
+    const float b = (e.bias != nullptr && col < N) ? __ldg(e.bias + col) : 0.0f;
+    for (int rr = 0; rr < 32; ++rr) {
+      const int row = row0 + rr;
+      if (row < M && col < N) {
+        float t = act_fast<ACT>(stage[rr * 36 + lane] + b) * sc;
+        if (e.resid != nullptr) t += e.resid[static_cast<size_t>(row) * e.ldr + col];
+        if (e.out_f32) reinterpret_cast<float*>(e.C)[static_cast<size_t>(row) * e.ldc + col] = t;
+        else reinterpret_cast<bf16*>(e.C)[static_cast<size_t>(row) * e.ldc + col] = __float2bfloat16_rn(t);
+      }
+    }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void epi_store_coalesced(const GemmEpi& e, float sc, int row0, int col0, int M, int N, float (&v)[32],
+                                                    float* stage, int lane) {
+  if (e.act == ACT_NONE) epi_store_coalesced_t<ACT_NONE>(e, sc, row0, col0, M, N, v, stage, lane);
+  else if (e.act == ACT_GELU) epi_store_coalesced_t<ACT_GELU>(e, sc, row0, col0, M, N, v, stage, lane);
+  else if (e.act == ACT_QUICKGELU) epi_store_coalesced_t<ACT_QUICKGELU>(e, sc, row0, col0, M, N, v, stage, lane);
+  else epi_store_coalesced_t<ACT_RELU>(e, sc, row0, col0, M, N, v, stage, lane);
+}
+
+struct GemmTc2 {
+  static constexpr int BM = 256, BN = 256, BK = 64, UMMA_K = 16;
+  static constexpr int A_BYTES = 128 * BK * 2;        // this CTA's 128 rows of A
+  static constexpr int B_BYTES = 128 * BK * 2;        // this CTA's half (128 N-rows) of B
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 5;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * 36 * 4;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmTc2::THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                int M_host, const int* __restrict__ m_dev, int m_mul, int N, int K, GemmEpi epi) {
+  using G = GemmTc2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  float* epi_stage = reinterpret_cast<float*>(smem + G::STAGES * G::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G::STAGES * G::STAGE_BYTES + G::EPI_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + G::STAGES;
+  uint64_t* tfull_bar = empty_bar + G::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int M = dyn_rows(M_host, m_dev, m_mul);
+  const int m_blocks = (M + G::BM - 1) / G::BM;
+  const int n_blocks = (N + G::BN - 1) / G::BN;
+  const int num_tiles = m_blocks * n_blocks;
+  const int num_kb = (K + G::BK - 1) / G::BK;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < G::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);                      // only the leader's is used: its own arrive.expect_tx
+      mbar_init(&empty_bar[s], 1);                     // one multicast tcgen05.commit per phase
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * G::EPI_WARPS);     // leader's: epilogue warps of BOTH CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, G::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (one per CTA): own A rows + own half of B; bytes are accounted on the leader's barrier =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sa = smem + s * G::STAGE_BYTES;
+          const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[s]), 0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * G::STAGE_BYTES);
+          tma_load_2d_2cta(sa, &tmA, lead_full, kb * G::BK, m_blk * G::BM + static_cast<int>(rank) * 128);
+          tma_load_2d_2cta(sa + G::A_BYTES, &tmB, lead_full, kb * G::BK, n_blk * G::BN + static_cast<int>(rank) * 128);
+          if (++s == G::STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: leader CTA only, one thread, drives both SMs' tensor cores =====
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(G::BM, G::BN);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty_bar[as], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * G::BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * G::STAGE_BYTES);
+          const uint64_t adesc = make_desc_sw128(a_addr);
+          const uint64_t bdesc = make_desc_sw128(a_addr + G::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < G::BK / G::UMMA_K; ++k)
+            umma_bf16_2cta(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2cta(&empty_bar[s]);
+          if (++s == G::STAGES) { s = 0; ph ^= 1u; }
+        }
+        umma_commit_2cta(&tfull_bar[as]);
+        if (++as == 2) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue warps (both CTAs): this CTA's 128 accumulator rows =====
+    const int ew = warp - 2;
+    const int lane_grp = warp & 3;
+    const int col_half = ew >> 2;
+    constexpr int CH = G::BN / 64;
+    float* stage = epi_stage + ew * (32 * 36);
+    const float sc = (epi.scale != nullptr) ? __ldg(epi.scale) : 1.0f;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const int row0 = m_blk * G::BM + static_cast<int>(rank) * 128 + lane_grp * 32;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(as * G::BN);
+#pragma unroll 1
+      for (int c = col_half * CH; c < (col_half + 1) * CH; ++c) {
+        float v[32];
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
+        tmem_ld_wait();
+        const int col0 = n_blk * G::BN + c * 32;
+        if (epi.dbg == 1) {
+          const int row = row0 + lane;
+          if (row < M && col0 < N) epi_store<32, true>(epi, sc, row, col0, N, v);
+        } else if (epi.dbg == 0) {
+          if (row0 < M && col0 < N) epi_store_coalesced(epi, sc, row0, col0, M, N, v, stage, lane);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+      if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, G::TMEM_COLS);
   }
 }
 

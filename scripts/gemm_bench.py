@@ -16,7 +16,11 @@ SHAPES = [  # name, M, N, K, act, resid(out_f32)
     ("xattn.q", 7168, 512, 2048, 0, False), ("head.lstm0", 224, 4096, 3072, 0, True),
 ]
 impl = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+only = sys.argv[2] if len(sys.argv) > 2 else None
+if only:
+    SHAPES = [x for x in SHAPES if x[0] == only]
 res = {}
+print("impl", impl, "(0 = auto: 2-CTA when eligible, 2 = force 1-CTA)")
 for name, M, N, K, act, resid in SHAPES:
     A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
     W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()

@@ -25,7 +25,8 @@ def _ref_gemm(A, W, bias, act, scale, resid):
 
 
 SHAPES = [(128, 256, 64), (128, 64, 128), (200, 512, 1024), (1000, 3072, 1024), (1028, 1024, 4096),
-          (32, 6144, 2048), (7, 4096, 3072), (300, 200, 136), (5000, 4096, 1024), (1, 6, 512), (38000, 1024, 640)]
+          (32, 6144, 2048), (7, 4096, 3072), (300, 200, 136), (5000, 4096, 1024), (1, 6, 512), (38000, 1024, 640),
+          (9000, 1000, 520), (256 * 74, 256, 64), (19999, 2048, 2048)]     # the last rows take the 2-CTA (cta_group::2) kernel
 
 
 @pytest.mark.parametrize("impl", ["simt", "tcgen05"])
@@ -44,10 +45,11 @@ def test_gemm_plain(impl, M, N, K):
 
 
 @pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+@pytest.mark.parametrize("M", [777, 5003])          # 5003 rows -> 2-CTA kernel with the smem-staged coalesced epilogue
 @pytest.mark.parametrize("act", [0, 1, 2, 3])
-def test_gemm_epilogues(impl, act):
+def test_gemm_epilogues(impl, act, M):
     from deer_vla_b200.engine import op_gemm
-    M, N, K = 777, 1000, 512
+    N, K = 1000, 512
     g = torch.Generator(device="cuda").manual_seed(act)
     A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
     W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
