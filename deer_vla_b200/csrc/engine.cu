@@ -839,6 +839,7 @@ template <typename T> struct StepImpl {
     const int nl = c->nl, inner = c->inner, kvr = np + nl;
     broadcast_rows_kernel<<<1184, 256, 0, st>>>(c->p_latents, c->lat, (size_t)nl * Wd, (size_t)NI * nl * Wd);
     KLAUNCH_CHECK("latents_init");
+    c->gemm.tag = 1;
     for (int i = 0; i < f.perc_depth; ++i) {
       const PercLayerW& w = c->perc[i];
       // norm_media(x): read the patch tokens straight out of the ViT residual stream (skip CLS), write rows [0,np) of each kv block

@@ -1,0 +1,119 @@
+"""``ModelWrapper`` (robot_flamingo/eval/eval_utils.py:187-490): the CALVIN policy adapter, on the engine.
+
+``step(obs, goal)`` keeps the reference contract -- uint8 camera frames + an instruction string in, a
+``(multi_execution, 7)`` float16 numpy action out -- and ``reset()`` clears the episode's LSTM state.
+``BatchedModelWrapper`` steps N environments in lock-step through one engine call (slots = environments).
+Image preprocessing here is the open_clip transform restated in torch (bicubic resize to 224, center crop,
+CLIP mean/std); it is outside the device-timed hot path.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .weights import CLIP_MEAN, CLIP_STD
+
+
+def clip_image_transform(image_size: int = 224) -> Callable:
+    """uint8 HWC numpy / PIL image -> (3, image_size, image_size) f32, like open_clip's image_transform(is_train=False)."""
+    mean = torch.tensor(CLIP_MEAN).view(3, 1, 1)
+    std = torch.tensor(CLIP_STD).view(3, 1, 1)
+
+    def fn(img) -> torch.Tensor:
+        a = torch.from_numpy(np.asarray(img)).permute(2, 0, 1).float().unsqueeze(0) / 255.0
+        h, w = a.shape[-2:]
+        s = image_size / min(h, w)
+        nh, nw = max(image_size, round(h * s)), max(image_size, round(w * s))
+        a = F.interpolate(a, size=(nh, nw), mode="bicubic", align_corners=False, antialias=True).clamp_(0, 1)
+        t, l = (nh - image_size) // 2, (nw - image_size) // 2
+        a = a[0, :, t:t + image_size, l:l + image_size]
+        return ((a - mean) / std).contiguous()
+    return fn
+
+
+def preprocess_image(sample, image_processor) -> torch.Tensor:          # data.py:898-902
+    return torch.cat([image_processor(s).unsqueeze(0) for s in sample], dim=0)
+
+
+def preprocess_text_calvin(sample: Sequence[str], tokenizer):           # data.py:905-919
+    tokenizer.padding_side = "right"
+    sample = [f"<image>{s.strip()}<|endofchunk|>{tokenizer.eos_token}" for s in sample]
+    text = tokenizer(sample, max_length=32, padding="longest", truncation="only_first", return_tensors="pt")
+    return text["input_ids"], text["attention_mask"]
+
+
+def postprocess_action(pose: torch.Tensor, gripper: torch.Tensor, multi_execution: int = 1) -> np.ndarray:
+    """eval_utils.py:454-477 (act_step == 1): cat(pose, gripper>0.5)[-1]; gripper -> +-1; repeat; fp16 numpy."""
+    action = torch.cat((pose.reshape(-1, 6), (gripper.reshape(-1, 1) > 0.5).float()), dim=1)[-1]
+    action[-1] = (action[-1] - 0.5) * 2
+    action = torch.stack([action] * multi_execution, dim=0)
+    return action.cpu().detach().to(dtype=torch.float16).numpy()
+
+
+class ModelWrapper:
+    def __init__(self, model, tokenizer, image_processor, cast_dtype=None, use_diff=False, history_len=None, future_act_len=-1,
+                 amp=False, exit_id=None, early_exit=False, exit_controller=None, multi_execution=1, use_action_ensemble=False):
+        assert not use_diff and not use_action_ensemble, "deterministic LSTM head only (eval_calvin.py:201,315)"
+        self.model = model
+        self.replan = model.module.replan
+        self.decoder_type = model.module.decoder_type
+        self.head_type = model.module.head_type
+        self.fusion_mode = model.module.fusion_mode
+        self.text_process_fn = lambda goals: preprocess_text_calvin(goals, tokenizer)
+        self.image_process_fn = lambda imgs: preprocess_image(imgs, image_processor)
+        self.amp, self.exit_id = amp, exit_id
+        self.dynamic_early_exit, self.exit_controller = early_exit, exit_controller
+        self.multi_execution = multi_execution
+        self.current_exit_layer = exit_id if isinstance(exit_id, int) else -1
+        assert model.module.act_step == 1
+        self.device = model.module.engine.device
+
+    def reset(self):                                                    # eval_utils.py:252-277
+        self.model.module.clear_all_exit_memory()
+
+    def step(self, obs, goal, get_action=True):                         # eval_utils.py:279-490
+        if not get_action:
+            return None
+        image_x = self.image_process_fn([obs["rgb_obs"]["rgb_static"]]).unsqueeze(1).unsqueeze(1)
+        gripper = self.image_process_fn([obs["rgb_obs"]["rgb_gripper"]]).unsqueeze(1).unsqueeze(1)
+        text_x, mask = self.text_process_fn([goal])
+        assert self.model.module.pad_length == -1
+        window_size = self.model.module.set_all_exit_window_size(1)
+        out = self.model(vision_x=image_x.to(self.device), lang_x=text_x.to(self.device), attention_mask=mask.to(self.device),
+                         vision_gripper=gripper.to(self.device), state_tensor=None, return_feature=True, deterministic=True,
+                         exit_id=self.exit_id, dynamic_early_exit=self.dynamic_early_exit, exit_controller=self.exit_controller)
+        self.current_exit_layer = out.exit_layer
+        action = postprocess_action(out.logits[0], out.logits[1], self.multi_execution)
+        self.model.module.set_all_exit_window_size(window_size)
+        return action
+
+
+class BatchedModelWrapper:
+    """N environments in lock-step: one ``deer_step`` per environment step.  ``reset(i)`` clears one env's
+    LSTM slot (a new subtask rollout, eval_utils.py:646)."""
+
+    def __init__(self, model, tokenizer, image_processor, exit_controller=None, multi_execution=1):
+        self.model, self.exit_controller, self.multi_execution = model, exit_controller, multi_execution
+        self.text_process_fn = lambda goals: preprocess_text_calvin(goals, tokenizer)
+        self.image_process_fn = lambda imgs: preprocess_image(imgs, image_processor)
+        self.device = model.module.engine.device
+        self.current_exit_layers: Optional[List[int]] = None
+
+    def reset(self, env_ids: Optional[Sequence[int]] = None):
+        self.model.module.engine.reset(env_ids)
+
+    def step(self, obs_list, goals: Sequence[str], env_ids: Optional[Sequence[int]] = None) -> np.ndarray:
+        n = len(obs_list)
+        rgb = self.image_process_fn([o["rgb_obs"]["rgb_static"] for o in obs_list]).view(n, 1, 1, 3, *([self.model.module.cfg.image_size] * 2))
+        grip = self.image_process_fn([o["rgb_obs"]["rgb_gripper"] for o in obs_list]).view(n, 1, 1, 3, *([self.model.module.cfg.image_size] * 2))
+        ids, mask = self.text_process_fn(list(goals))
+        slots = None if env_ids is None else torch.tensor(list(env_ids), dtype=torch.int32, device=self.device)
+        out = self.model(vision_x=rgb.to(self.device), lang_x=ids.to(self.device), attention_mask=mask.to(self.device),
+                         vision_gripper=grip.to(self.device), dynamic_early_exit=self.exit_controller is not None,
+                         exit_controller=self.exit_controller, slots=slots)
+        self.current_exit_layers = out.exit_layers.cpu().tolist()
+        a = out.action.cpu()
+        return torch.stack([a] * self.multi_execution, dim=1).to(torch.float16).numpy()      # (n, multi_execution, 7)

@@ -5,13 +5,14 @@
 631-638; eval_calvin.py:541-577), so a real checkpoint can be passed to
 ``DeerEngine.load_state_dict`` unchanged.  No real checkpoints exist in the build environment, so
 ``synth_state_dict`` draws seeded synthetic values (one generator per tensor, seeded by
-(seed, index)): Linear/Embedding N(0,0.02), LayerNorm gamma 1+0.1N / beta 0.1N, LSTM
+(seed, crc32(name)), so the tensors of a truncated model equal those of the full one): Linear/Embedding N(0,0.02), LayerNorm gamma 1+0.1N / beta 0.1N, LSTM
 U(+-1/sqrt(H)), Perceiver latents N(0,1), non-zero tanh gates (helpers.py:255,258 initialise the
 gates to 0, which would null the cross-attention path).
 """
 from __future__ import annotations
 
 import math
+import zlib
 from typing import Dict, List, Tuple
 
 import torch
@@ -94,7 +95,7 @@ def synth_state_dict(cfg: DeerConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
     out: Dict[str, torch.Tensor] = {}
     gi = 0
     for idx, (name, shape, kind) in enumerate(state_dict_spec(cfg)):
-        g = torch.Generator().manual_seed(seed * 1000003 + idx)
+        g = torch.Generator().manual_seed(seed * 1000003 + zlib.crc32(name.encode()))
         if kind == "w":
             t = torch.randn(shape, generator=g) * 0.02
         elif kind == "wout":

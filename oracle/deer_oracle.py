@@ -23,6 +23,7 @@ Pinning status (see ``oracle/make_golden.py`` and ``DESIGN.md``):
 from __future__ import annotations
 
 import math
+import zlib
 from dataclasses import dataclass, field, asdict
 from typing import Dict, List, Optional, Tuple
 
@@ -221,12 +222,12 @@ def weight_specs(cfg: DeerConfig) -> List[Tuple[str, Tuple[int, ...], str]]:
 def synth_weights(cfg: DeerConfig, seed: int = 0) -> Dict[str, Tensor]:
     """Seeded synthetic weights, generated in ``weight_specs`` order (there are no real
     checkpoints in the build environment).  Each tensor uses its own generator seeded by
-    (seed, index) so a subset can be regenerated without the rest."""
+    (seed, crc32(name)): a model truncated by max_layer gets the same tensors as the full one."""
     out: Dict[str, Tensor] = {}
     gate_vals = [0.5, -0.4, 0.7, 0.35, -0.6, 0.45]
     gi = 0
     for idx, (name, shape, kind) in enumerate(weight_specs(cfg)):
-        g = torch.Generator().manual_seed(seed * 1000003 + idx)
+        g = torch.Generator().manual_seed(seed * 1000003 + zlib.crc32(name.encode()))
         if kind == "w":
             t = torch.randn(shape, generator=g) * 0.02
         elif kind == "wout":

@@ -1,0 +1,106 @@
+"""CPU tests of the product's host-side logic (no GPU, no CUDA calls)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import deer_oracle as O
+
+
+def test_product_config_agrees_with_oracle_bookkeeping():
+    from deer_vla_b200 import config_3b, config_9b, config_tiny
+    for pc, oc in ((config_3b(12), O.config_3b(12)), (config_3b(4), O.config_3b(4)), (config_9b(12), O.config_9b(12)),
+                   (config_9b(8), O.config_9b(8)), (config_tiny(), O.config_tiny()), (config_3b(24), O.config_3b(24))):
+        assert pc.to_dict() == oc.to_dict()
+        assert (pc.n_layers, pc.exit_list, pc.ctrl_max_layer, pc.n_thresholds) == (oc.n_layers, oc.exit_list, oc.ctrl_max_layer, oc.n_thresholds)
+
+
+def test_synthetic_checkpoint_generators_agree():
+    from deer_vla_b200 import DeerConfig
+    from deer_vla_b200.weights import state_dict_spec, synth_state_dict
+    oc = O.config_tiny()
+    W = O.synth_weights(oc, 3)
+    P = synth_state_dict(DeerConfig(**oc.to_dict()), 3)
+    assert list(W) == list(P) and all(torch.equal(W[k], P[k]) for k in W)
+    spec9 = {n for n, _, _ in state_dict_spec(DeerConfig(**O.config_9b(12).to_dict()))}
+    assert "lang_encoder.transformer.blocks.3.gated_cross_attn_layer.attn.to_q.weight" in spec9
+    assert "lang_encoder.transformer.blocks.2.gated_cross_attn_layer.attn.to_q.weight" not in spec9
+    assert "lang_encoder.transformer.blocks.0.decoder_layer.norm_1.weight" in spec9
+
+
+def test_exit_controller_threshold_solver_matches_reference(gold_thr):
+    """The product's vectorised solver vs thresholds produced by the reference's ExitController.set_threshold."""
+    from deer_vla_b200.value_net import ExitController, solve_thresholds
+    g = gold_thr
+    for name, llm in (("3b", "mpt_dolly_3b"), ("3b_s", "mpt_dolly_3b"), ("9b", "mpt_9b")):
+        values = torch.from_numpy(g[f"{name}_values"])
+        for ratio in (0.5, 0.8, 1.0, 1.5, 2.0):
+            for dist in ("exp", "gauss", "gamma"):
+                T = solve_thresholds(values, ratio, dist, llm)
+                assert np.array_equal(T.double().numpy(), g[f"{name}_{dist}_{ratio}"]), (name, ratio, dist)
+    n_exit = g["3b_values"].shape[0]
+    exits = list(range(1, 2 * n_exit, 2))
+    ctrl = ExitController(None, exit_id_list=exits, steps_per_stage=1, exit_dist="exp", leq=True, max_layer=exits[-1] + 1)
+    ctrl.set_threshold(None, None, None, 1.0, "mpt_dolly_3b", values=torch.from_numpy(g["3b_values"]))
+    assert [ctrl.thresholds[e] for e in exits] == [float(x) for x in g["3b_exp_1.0"]]
+    with pytest.raises(AssertionError):
+        ctrl._set_threshold_value([0.1, 0.2])            # len(thresholds) == real_num_exit (value_net.py:179)
+    ctrl.set_timestep(5)
+    assert ctrl.cur_step == 5 and ctrl.module is ctrl
+
+
+def test_exit_controller_max_layer_semantics():
+    from deer_vla_b200.value_net import ExitController
+    c = ExitController(None, exit_id_list=[1, 3, 4], max_layer=4)        # DeeR-S
+    assert c.max_layer == 3 and c._real_exits() == [1, 3]
+    c = ExitController(None, exit_id_list=[1, 3, 5, 7, 9, 11], max_layer=12)
+    assert c.max_layer == 11 and len(c._real_exits()) == 6
+    c = ExitController(None, exit_id_list=[1, 3, 5, 7, 9, 11], max_layer=24)
+    assert c.max_layer == 11
+
+
+def test_sharding_block_split():
+    from deer_vla_b200.sharding import owner_of, shard_sequences
+    seqs = list(range(224))
+    parts = [shard_sequences(seqs, r, 8) for r in range(8)]
+    assert all(len(p) == 28 for p in parts) and sum(parts, []) == seqs
+    assert owner_of(27, 224, 8) == 0 and owner_of(28, 224, 8) == 1 and owner_of(223, 224, 8) == 7
+    with pytest.raises(AssertionError):
+        shard_sequences(list(range(10)), 0, 4)            # NUM_SEQUENCES % device_num == 0 (eval_utils.py:523)
+
+
+class _Tok:
+    eos_token = "<eos>"
+    padding_side = "left"
+
+    def __call__(self, sample, max_length, padding, truncation, return_tensors):
+        ids = [[7] + [ord(c) % 50 + 10 for c in s][: max_length - 1] for s in sample]
+        L = max(len(i) for i in ids)
+        mask = [[1] * len(i) + [0] * (L - len(i)) for i in ids]
+        ids = [i + [0] * (L - len(i)) for i in ids]
+        return {"input_ids": torch.tensor(ids), "attention_mask": torch.tensor(mask)}
+
+
+def test_text_and_action_processing():
+    from deer_vla_b200.eval_utils import clip_image_transform, postprocess_action, preprocess_text_calvin
+    tok = _Tok()
+    ids, mask = preprocess_text_calvin(["  push the block  ", "lift"], tok)
+    assert tok.padding_side == "right" and ids.shape == mask.shape and ids.shape[1] <= 32
+    a = postprocess_action(torch.tensor([[[0.1, -0.2, 0.3, 0.0, 0.5, -0.9]]]), torch.tensor([[[0.7]]]), multi_execution=2)
+    assert a.dtype == np.float16 and a.shape == (2, 7) and a[0, 6] == 1.0
+    a = postprocess_action(torch.zeros(1, 1, 6), torch.tensor([[[0.5]]]))        # gripper > 0.5 is strict (eval_utils.py:458)
+    assert a[0, 6] == -1.0
+    img = (np.random.RandomState(0).rand(200, 200, 3) * 255).astype(np.uint8)
+    t = clip_image_transform(224)(img)
+    assert t.shape == (3, 224, 224) and t.dtype == torch.float32
+    g = clip_image_transform(224)((np.random.RandomState(1).rand(84, 84, 3) * 255).astype(np.uint8))
+    assert g.shape == (3, 224, 224)
+
+
+def test_engine_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from deer_vla_b200 import config_tiny
+    from deer_vla_b200._lib import DeerError
+    from deer_vla_b200.engine import DeerEngine
+    with pytest.raises(DeerError, match="no CUDA device"):
+        DeerEngine(config_tiny(), max_batch=1)
