@@ -140,7 +140,7 @@ static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int
       return set_err(g.err, DEER_E_INVALID, "tcgen05 GEMM needs 16-byte aligned operands (lda=%d ldw=%d)", lda, ldw);
     const int mt = (M + 127) / 128;
     int BN;
-    const bool use2 = (impl != 2) && N >= 256 && ((M + 255) / 256) * ((N + 255) / 256) >= DEER_NUM_SMS / 2;
+    const bool use2 = (impl != 2) && N >= 256 && ((M + 255) / 256) * ((N + 255) / 256) >= 32;
     if (use2) BN = 128;                       // B box = this CTA's 128-row half of the 256-wide tile
     else if (mt * ((N + 255) / 256) >= 2 * DEER_NUM_SMS && N >= 256) BN = 256;
     else if (mt * ((N + 127) / 128) >= DEER_NUM_SMS && N >= 128) BN = 128;
@@ -263,6 +263,7 @@ struct deer_ctx {
   // taps
   float *tap_vit = nullptr, *tap_media = nullptr, *tap_hidden = nullptr, *tap_pooled = nullptr;
   int tap_n = 0, tap_S = 0;
+  int vit_chunk = 0;           // images per ViT pass (0 = all at once); DEER_VIT_CHUNK overrides
   cudaStream_t own_stream = nullptr;
   int* nact_hist = nullptr;            // device [16]: active count after each probe of the last step
   int n_probes_last = 0, n_last = 0;
@@ -428,6 +429,7 @@ extern "C" int deer_create(const deer_config* cfg, int device, deer_ctx** out) {
   if (r != DEER_OK) { g_last_error = c->err; delete c; return r; }
   cudaSetDevice(device);
   build_required(c);
+  c->vit_chunk = getenv("DEER_VIT_CHUNK") ? atoi(getenv("DEER_VIT_CHUNK")) : 0;
   c->gemm.stats = &c->stats;
   c->gemm.err = &c->err;
   const deer_config& f = c->cfg;
@@ -816,20 +818,28 @@ template <typename T> struct StepImpl {
     RET(gemm(c->im_cols, c->Kp, NImax * np, c->w_conv, c->Kp, NI * np, Wd, c->Kp, c->patch_out, Wd, 0, nullptr, ACT_NONE, nullptr, nullptr, 0, nullptr, 0));
     vit_assemble_kernel<T><<<NI * L, 128, 0, st>>>(tp(c->patch_out), c->v_cls, c->v_pos, c->v_lnpre_g, c->v_lnpre_b, c->vx, NI, L, Wd);
     KLAUNCH_CHECK("vit_assemble");
-    const int M = NI * L, Mmax = NImax * L;
+    const int Mmax = NImax * L;
     const LnMap id{0, 0, 0};
-    for (int i = 0; i < f.vit_layers; ++i) {
-      const VitLayerW& w = c->vit[i];
-      RET(ln<float, T>(c->vx, Wd, w.ln1_g, w.ln1_b, 1, Wd, tp(c->v_ln), Wd, id, nullptr, 0, 0, M, nullptr, 0));
-      RET(gemm(c->v_ln, Wd, Mmax, w.w_in, Wd, M, 3 * Wd, Wd, c->v_qkv, 3 * Wd, 0, w.b_in, ACT_NONE, nullptr, nullptr, 0, nullptr, 0));
-      AttnParams a{};
-      a.Q = c->v_qkv; a.K = tp(c->v_qkv) + Wd; a.V = tp(c->v_qkv) + 2 * Wd; a.O = c->v_att;
-      a.ldq = a.ldk = a.ldv = 3 * Wd; a.ldo = Wd; a.Sq = a.Sk = L; a.H = f.vit_heads; a.hd = 64; a.scale = 0.125f; a.B_host = NI;
-      RET(run_attention(0, c->dtype, a, &c->err, &c->stats, st));
-      RET(gemm(c->v_att, Wd, Mmax, w.w_out, Wd, M, Wd, Wd, c->vx, Wd, 1, w.b_out, ACT_NONE, nullptr, c->vx, Wd, nullptr, 0));
-      RET(ln<float, T>(c->vx, Wd, w.ln2_g, w.ln2_b, 1, Wd, tp(c->v_ln), Wd, id, nullptr, 0, 0, M, nullptr, 0));
-      RET(gemm(c->v_ln, Wd, Mmax, w.w_fc, Wd, M, f.vit_mlp, Wd, c->v_h, f.vit_mlp, 0, w.b_fc, ACT_QUICKGELU, nullptr, nullptr, 0, nullptr, 0));
-      RET(gemm(c->v_h, f.vit_mlp, Mmax, w.w_proj, f.vit_mlp, M, Wd, f.vit_mlp, c->vx, Wd, 1, w.b_proj, ACT_NONE, nullptr, c->vx, Wd, nullptr, 0));
+    // The 24 ViT blocks run over CHUNKS of images: the chunk's residual stream and the (re-used) ln / qkv / attention /
+    // MLP scratch stay resident in the 126 MB L2 from one GEMM to the next instead of round-tripping through HBM.
+    const int chunk = (c->vit_chunk > 0) ? std::min(c->vit_chunk, NI) : NI;
+    for (int i0 = 0; i0 < NI; i0 += chunk) {
+      const int nc = std::min(chunk, NI - i0);
+      const int M = nc * L;
+      float* vxc = c->vx + (size_t)i0 * L * Wd;
+      for (int i = 0; i < f.vit_layers; ++i) {
+        const VitLayerW& w = c->vit[i];
+        RET(ln<float, T>(vxc, Wd, w.ln1_g, w.ln1_b, 1, Wd, tp(c->v_ln), Wd, id, nullptr, 0, 0, M, nullptr, 0));
+        RET(gemm(c->v_ln, Wd, Mmax, w.w_in, Wd, M, 3 * Wd, Wd, c->v_qkv, 3 * Wd, 0, w.b_in, ACT_NONE, nullptr, nullptr, 0, nullptr, 0));
+        AttnParams a{};
+        a.Q = c->v_qkv; a.K = tp(c->v_qkv) + Wd; a.V = tp(c->v_qkv) + 2 * Wd; a.O = c->v_att;
+        a.ldq = a.ldk = a.ldv = 3 * Wd; a.ldo = Wd; a.Sq = a.Sk = L; a.H = f.vit_heads; a.hd = 64; a.scale = 0.125f; a.B_host = nc;
+        RET(run_attention(0, c->dtype, a, &c->err, &c->stats, st));
+        RET(gemm(c->v_att, Wd, Mmax, w.w_out, Wd, M, Wd, Wd, vxc, Wd, 1, w.b_out, ACT_NONE, nullptr, vxc, Wd, nullptr, 0));
+        RET(ln<float, T>(vxc, Wd, w.ln2_g, w.ln2_b, 1, Wd, tp(c->v_ln), Wd, id, nullptr, 0, 0, M, nullptr, 0));
+        RET(gemm(c->v_ln, Wd, Mmax, w.w_fc, Wd, M, f.vit_mlp, Wd, c->v_h, f.vit_mlp, 0, w.b_fc, ACT_QUICKGELU, nullptr, nullptr, 0, nullptr, 0));
+        RET(gemm(c->v_h, f.vit_mlp, Mmax, w.w_proj, f.vit_mlp, M, Wd, f.vit_mlp, vxc, Wd, 1, w.b_proj, ACT_NONE, nullptr, vxc, Wd, nullptr, 0));
+      }
     }
     if (f.debug_taps) {
       vit_tokens_kernel<<<1184, 256, 0, st>>>(c->vx, c->tap_vit, NI, L, Wd);

@@ -20,7 +20,7 @@ struct GemmEpi {
   const float* scale;  // device scalar (e.g. tanh(attn_gate)) or nullptr
   const float* resid;  // fp32 [M, ldr] or nullptr (may alias C)
   int ldr;
-  int dbg;             // 0 normal; tuning only: 1 = direct (row-per-thread) stores in the 2-CTA kernel, 2 = skip stores
+  int dbg;             // 0 normal; tuning only: 2 = skip the epilogue's math and stores in the 2-CTA kernel (mainloop-only timing)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -423,34 +423,37 @@ __device__ __forceinline__ void epi_store_coalesced_t(const GemmEpi& e, float sc
   const bool vec_ok = fullc && ((e.ldc & 7) == 0) && (e.resid == nullptr || (e.ldr & 3) == 0);
   const int sub = lane >> 3, c4 = (lane & 7) * 4;
   float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 rs[8];
-  if (vec_ok) {
-    if (e.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + c4));
-    if (e.resid != nullptr) {
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int row = row0 + it * 4 + sub;
-        rs[it] = (row < M) ? *reinterpret_cast<const float4*>(e.resid + static_cast<size_t>(row) * e.ldr + col0 + c4)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-  }
+  const bool has_res = vec_ok && (e.resid != nullptr);
+  if (vec_ok && e.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + c4));
 #pragma unroll
   for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stage + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
   __syncwarp();
   if (vec_ok) {
+    // v[] is dead from here on: the residual rows are fetched in two batches of four 128-byte row segments per 8 lanes
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + sub;
-      const int row = row0 + rr;
-      float4 t = epi_math4<ACT>(*reinterpret_cast<const float4*>(stage + rr * 36 + c4), b4, sc);
-      if (row < M) {
-        if (e.resid != nullptr) { t.x += rs[it].x; t.y += rs[it].y; t.z += rs[it].z; t.w += rs[it].w; }
-        if (e.out_f32) {
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.C) + static_cast<size_t>(row) * e.ldc + col0 + c4) = t;
-        } else {
-          uint2 o; o.x = pack_bf16x2(t.x, t.y); o.y = pack_bf16x2(t.z, t.w);
-          *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.C) + static_cast<size_t>(row) * e.ldc + col0 + c4) = o;
+    for (int half = 0; half < 2; ++half) {
+      float4 rs[4];
+      if (has_res) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int row = row0 + (half * 4 + it) * 4 + sub;
+          rs[it] = (row < M) ? *reinterpret_cast<const float4*>(e.resid + static_cast<size_t>(row) * e.ldr + col0 + c4)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = (half * 4 + it) * 4 + sub;
+        const int row = row0 + rr;
+        float4 t = epi_math4<ACT>(*reinterpret_cast<const float4*>(stage + rr * 36 + c4), b4, sc);
+        if (row < M) {
+          if (has_res) { t.x += rs[it].x; t.y += rs[it].y; t.z += rs[it].z; t.w += rs[it].w; }
+          if (e.out_f32) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.C) + static_cast<size_t>(row) * e.ldc + col0 + c4) = t;
+          } else {
+            uint2 o; o.x = pack_bf16x2(t.x, t.y); o.y = pack_bf16x2(t.z, t.w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.C) + static_cast<size_t>(row) * e.ldc + col0 + c4) = o;
+          }
         }
       }
     }
@@ -483,7 +486,7 @@ struct GemmTc2 {
   static constexpr int B_BYTES = 128 * BK * 2;        // this CTA's half (128 N-rows) of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = 5;
-  static constexpr int EPI_WARPS = 8;
+  static constexpr int EPI_WARPS = 12;                // three warps per TMEM lane quarter; 448 threads -> 128 registers each
   static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * 36 * 4;
   static constexpr int TMEM_COLS = 512;
   static constexpr int BAR_BYTES = 256;
@@ -585,8 +588,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===== epilogue warps (both CTAs): this CTA's 128 accumulator rows =====
     const int ew = warp - 2;
     const int lane_grp = warp & 3;
-    const int col_half = ew >> 2;
-    constexpr int CH = G::BN / 64;
+    const int col_part = ew >> 2;                       // 0..2: the eight 32-column chunks are split 3 / 3 / 2
+    const int c_begin = col_part * 3, c_end = (col_part == 2) ? 8 : c_begin + 3;
     float* stage = epi_stage + ew * (32 * 36);
     const float sc = (epi.scale != nullptr) ? __ldg(epi.scale) : 1.0f;
     int as = 0;
@@ -598,17 +601,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int row0 = m_blk * G::BM + static_cast<int>(rank) * 128 + lane_grp * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(as * G::BN);
 #pragma unroll 1
-      for (int c = col_half * CH; c < (col_half + 1) * CH; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         float v[32];
         tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
         tmem_ld_wait();
         const int col0 = n_blk * G::BN + c * 32;
-        if (epi.dbg == 1) {
-          const int row = row0 + lane;
-          if (row < M && col0 < N) epi_store<32, true>(epi, sc, row, col0, N, v);
-        } else if (epi.dbg == 0) {
-          if (row0 < M && col0 < N) epi_store_coalesced(epi, sc, row0, col0, M, N, v, stage, lane);
-        }
+        if (epi.dbg == 0 && row0 < M && col0 < N) epi_store_coalesced(epi, sc, row0, col0, M, N, v, stage, lane);
       }
       tc_fence_before();
       __syncwarp();
