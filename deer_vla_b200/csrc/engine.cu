@@ -2,6 +2,7 @@
 // See include/deer_engine.h for the contract and DESIGN.md for the data layout.
 #include "../../include/deer_engine.h"
 #include "attention.cuh"
+#include "attn_tc.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
 
@@ -173,9 +174,46 @@ static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int
   return DEER_OK;
 }
 
+static std::map<TmapKey, CUtensorMap> g_attn_tmaps;
+static const CUtensorMap* attn_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box) {
+  TmapKey k{ptr, rows, cols, ld, box};
+  auto it = g_attn_tmaps.find(k);
+  if (it == g_attn_tmaps.end()) {
+    CUtensorMap tm;
+    if (!make_tmap(&tm, ptr, rows, cols, ld, box)) return nullptr;
+    if (g_attn_tmaps.size() > 4096) g_attn_tmaps.clear();
+    it = g_attn_tmaps.emplace(k, tm).first;
+  }
+  return &it->second;
+}
+
+// impl: 0 = tensor-core path (tcgen05 kernel when the shape allows, else the mma.sync flash kernel), 1 = SIMT reference,
+//       2 = on-chip small-attention kernel (LLM layers), 3 = force the mma.sync flash kernel
 static int run_attention(int impl, int dtype, const AttnParams& p, std::string* err, LaunchStats* stats, cudaStream_t st) {
   if (p.B_host <= 0) return DEER_OK;
-  if (impl == 0 && dtype == 0 && p.hd == 64 && !p.causal && !p.alibi_slopes && !p.kv_len && !p.qmode && !p.n_dev && p.ldk == p.ldv) {
+  const bool plain = dtype == 0 && p.hd == 64 && !p.causal && !p.alibi_slopes && !p.kv_len && !p.qmode && !p.n_dev && p.ldk == p.ldv;
+  static const bool no_tc = getenv("DEER_ATTN_NO_TC") != nullptr;
+  bool done = false;
+  if (impl == 0 && plain && !no_tc && p.Sk <= AttnTc::SKP && (p.ldq % 8) == 0 && (p.ldk % 8) == 0 && (p.ldo % 8) == 0) {
+    const uint64_t width = (uint64_t)p.H * 64;
+    const CUtensorMap* tq = attn_tmap(p.Q, (uint64_t)p.B_host * p.Sq, width, p.ldq, 128);
+    const CUtensorMap* tk = attn_tmap(p.K, (uint64_t)p.B_host * p.Sk, width, p.ldk, AttnTc::HALF_ROWS);
+    const CUtensorMap* tv = attn_tmap(p.V, (uint64_t)p.B_host * p.Sk, width, p.ldv, AttnTc::HALF_ROWS);
+    if (tq && tk && tv) {
+      static bool attr_done = false;
+      if (!attr_done) {
+        cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTc::SMEM_BYTES);
+        attr_done = true;
+      }
+      const int grid = std::min(p.B_host * p.H, DEER_NUM_SMS);
+      attn_tc_kernel<<<grid, AttnTc::THREADS, AttnTc::SMEM_BYTES, st>>>(*tq, *tk, *tv, reinterpret_cast<const bf16*>(p.Q), p.ldq,
+                                                                        reinterpret_cast<bf16*>(p.O), p.ldo, p.B_host, p.H, p.Sq, p.Sk,
+                                                                        p.scale * 1.4426950408889634f);
+      done = true;
+    }
+  }
+  if (done) {
+  } else if ((impl == 0 || impl == 3) && plain) {
     dim3 grid((p.Sq + 63) / 64, p.H, p.B_host);
     flash_attn_hd64_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const bf16*>(p.Q), p.ldq, reinterpret_cast<const bf16*>(p.K),
                                                  reinterpret_cast<const bf16*>(p.V), p.ldk, reinterpret_cast<bf16*>(p.O), p.ldo, p.Sq, p.Sk,
@@ -1201,9 +1239,23 @@ extern "C" int deer_op_gemm(int impl, int dtype, const void* A, int lda, const v
 extern "C" int deer_op_attention(int impl, int dtype, const void* Q, int ldq, const void* K, const void* V, int ldk, void* O, int ldo, int B, int H,
                                  int Sq, int Sk, int head_dim, float scale, void* stream) {
   if (!Q || !K || !V || !O) return set_err(nullptr, DEER_E_INVALID, "null pointer");
-  if (impl == 0 && (dtype != 0 || head_dim != 64)) return set_err(nullptr, DEER_E_INVALID, "flash kernel needs bf16 and head_dim 64");
+  if ((impl == 0 || impl == 3) && (dtype != 0 || head_dim != 64)) return set_err(nullptr, DEER_E_INVALID, "tensor-core attention needs bf16 and head_dim 64");
   AttnParams a{};
   a.Q = Q; a.K = K; a.V = V; a.O = O; a.ldq = ldq; a.ldk = a.ldv = ldk; a.ldo = ldo; a.Sq = Sq; a.Sk = Sk; a.H = H; a.hd = head_dim;
   a.scale = scale; a.B_host = B;
   return run_attention(impl, dtype, a, &g_op_err, nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// bring-up probe for the tensor-core attention: O = P @ V with P in TMEM (A operand) and V as an MN-major B operand
+extern "C" int deer_op_pv_probe(const void* P, const void* V, float* O, int K, int lbo_bytes, int sbo_bytes, int kstep_bytes, void* stream) {
+  if (!P || !V || !O || K % 16 || K > 256) return set_err(nullptr, DEER_E_INVALID, "bad pv probe arguments");
+  CUtensorMap tm;
+  if (!make_tmap(&tm, V, K, 64, 64, (uint32_t)K)) return set_err(nullptr, DEER_E_CUDA, "tensor map for V failed");
+  const int smem = 256 * 128 + 1024 + 64;
+  cudaFuncSetAttribute(pv_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  pv_probe_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tm, reinterpret_cast<const bf16*>(P), O, K, (uint32_t)lbo_bytes,
+                                                                           (uint32_t)sbo_bytes, (uint32_t)kstep_bytes);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(nullptr, DEER_E_CUDA, "pv probe launch failed: %s", cudaGetErrorString(e));
+  return DEER_OK;
 }

@@ -243,7 +243,7 @@ def op_gemm(A: torch.Tensor, W: torch.Tensor, bias=None, act: int = 0, scale=Non
     return Cm
 
 
-def op_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, impl: str = "flash") -> torch.Tensor:
+def op_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, impl: str = "tc") -> torch.Tensor:
     """q [B,Sq,H,hd], k/v [B,Sk,H,hd] (contiguous) -> [B,Sq,H,hd] through ``deer_op_attention`` (no mask)."""
     lib = _lib.load()
     B, Sq, H, hd = q.shape
@@ -254,7 +254,7 @@ def op_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float
     stream = torch.cuda.current_stream(q.device).cuda_stream
     kp = kv.data_ptr()
     vp = kp + H * hd * kv.element_size()
-    rc = lib.deer_op_attention({"flash": 0, "simt": 1}[impl], dtype, _ptr(q), H * hd, C.c_void_p(kp), C.c_void_p(vp), 2 * H * hd,
+    rc = lib.deer_op_attention({"tc": 0, "simt": 1, "flash": 3}[impl], dtype, _ptr(q), H * hd, C.c_void_p(kp), C.c_void_p(vp), 2 * H * hd,
                                _ptr(o), H * hd, B, H, Sq, Sk, hd, float(scale), C.c_void_p(stream))
     if rc != 0:
         raise DeerError(rc, lib.deer_last_error(None).decode())

@@ -181,10 +181,14 @@ int deer_get_stats(deer_ctx* ctx, deer_stats* out);
 int deer_op_gemm(int impl, int dtype, const void* A, int lda, const void* W, int ldw, void* C, int ldc,
                  int M, int N, int K, const float* bias, int act, const float* scale, const float* resid,
                  int out_f32, const int32_t* m_dev, int m_mul, void* stream);
-/* softmax(scale * Q K^T) V, no mask, head_dim 64, bf16 (impl 0 = tensor-core flash kernel, 1 = SIMT reference;
- * dtype as above, impl 0 requires bf16).  Q rows: (b*Sq+i)*ldq + h*64, K/V rows: (b*Sk+j)*ldk + h*64. */
+/* softmax(scale * Q K^T) V, no mask (impl 0 = tensor-core path: the tcgen05 kernel when Sk <= 272, else the mma.sync flash
+ * kernel; 1 = SIMT reference; 3 = force the mma.sync flash kernel; dtype as above, impl 0/3 require bf16 and head_dim 64).  Q rows: (b*Sq+i)*ldq + h*64, K/V rows: (b*Sk+j)*ldk + h*64. */
 int deer_op_attention(int impl, int dtype, const void* Q, int ldq, const void* K, const void* V, int ldk,
                       void* O, int ldo, int B, int H, int Sq, int Sk, int head_dim, float scale, void* stream);
+
+/* bring-up / regression probe of the tensor-core attention's second GEMM: O[128,64] = P[128,K] @ V[K,64] with P staged in
+ * tensor memory (tcgen05.st) as the A operand and V read in its natural [key][d] layout as an MN-major B operand. */
+int deer_op_pv_probe(const void* P, const void* V, float* O, int K, int lbo_bytes, int sbo_bytes, int kstep_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,27 @@
+"""ViT attention micro-benchmark through deer_op_attention (fused qkv layout like the engine's v_qkv buffer)."""
+import ctypes as C, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from deer_vla_b200 import _lib
+lib = _lib.load()
+B, H, S, W = 448, 16, 257, 1024
+qkv = torch.randn(B * S, 3 * W, device="cuda").bfloat16()
+out = torch.empty(B * S, W, device="cuda", dtype=torch.bfloat16)
+st = torch.cuda.current_stream().cuda_stream
+p = qkv.data_ptr()
+for name, impl in (("tcgen05", 0), ("mma.sync flash", 3)):
+    def run():
+        rc = lib.deer_op_attention(impl, 0, C.c_void_p(p), 3 * W, C.c_void_p(p + 2 * W), C.c_void_p(p + 4 * W), 3 * W, C.c_void_p(out.data_ptr()), W,
+                                   B, H, S, S, 64, 0.125, C.c_void_p(st))
+        assert rc == 0
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"{name:16s} {ms:7.3f} ms  {4 * B * H * S * S * 64 / ms / 1e9:7.1f} TFLOP/s")

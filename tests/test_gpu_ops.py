@@ -94,8 +94,9 @@ def _ref_attn(q, k, v, scale):
     return torch.einsum("bhij,bjhd->bihd", s.softmax(-1), v.float())
 
 
-@pytest.mark.parametrize("B,H,Sq,Sk", [(3, 4, 257, 257), (2, 8, 64, 320), (1, 2, 17, 17), (2, 16, 130, 70)])
-@pytest.mark.parametrize("impl", ["flash", "simt"])
+@pytest.mark.parametrize("B,H,Sq,Sk", [(3, 4, 257, 257), (2, 8, 64, 320), (1, 2, 17, 17), (2, 16, 130, 70), (40, 16, 257, 257),
+                                       (5, 3, 256, 272), (2, 2, 5, 9), (3, 2, 300, 200)])
+@pytest.mark.parametrize("impl", ["tc", "flash", "simt"])
 def test_attention_hd64(impl, B, H, Sq, Sk):
     from deer_vla_b200.engine import op_attention
     g = torch.Generator(device="cuda").manual_seed(B + H + Sq)
@@ -116,3 +117,19 @@ def test_attention_fp32_simt():
     v = torch.randn(2, 50, 3, 128, device="cuda", generator=g)
     out = op_attention(q, k, v, 1 / math.sqrt(128), impl="simt")
     assert (out - _ref_attn(q, k, v, 1 / math.sqrt(128))).abs().max().item() <= 1e-4
+
+
+def test_pv_probe_tmem_a_operand_and_mn_major_b():
+    """Regression for the two tcgen05 encodings the attention kernel relies on: P read from tensor memory (two bf16 per
+    32-bit column, lane = row) and V read in its natural [key][d] layout as an MN-major B operand (SBO 1024 B, 2048 B / 16 keys)."""
+    import ctypes as C
+    from deer_vla_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for K in (16, 64, 256):
+        P = torch.randn(128, K, device="cuda", generator=g).bfloat16()
+        V = torch.randn(K, 64, device="cuda", generator=g).bfloat16()
+        O = torch.zeros(128, 64, device="cuda")
+        assert lib.deer_op_pv_probe(C.c_void_p(P.data_ptr()), C.c_void_p(V.data_ptr()), C.c_void_p(O.data_ptr()), K, 1024, 1024, 2048, None) == 0
+        torch.cuda.synchronize()
+        assert (O - P.float() @ V.float()).abs().max().item() <= 1e-3 * K ** 0.5
