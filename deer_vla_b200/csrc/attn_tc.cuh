@@ -104,19 +104,27 @@ pv_probe_kernel(const __grid_constant__ CUtensorMap tmV, const bf16* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// attn_tc_kernel: softmax(scale * Q K^T) V on the 5th-gen tensor cores, head_dim 64, no mask, Sk <= 272 keys.
+// attn_tc_kernel: softmax(scale * Q K^T) V on the 5th-gen tensor cores, head_dim 64, no mask, Sk <= 264 keys.
 // (the ViT-L/14 attention: 257 x 257 per (image, head); ~3 % of a step's FLOPs but 18 % of its time on mma.sync)
 //
-// Persistent CTAs, one work item = one (batch, head): K and V are TMA-loaded ONCE per item in their natural [key][d]
-// layout (two 136-row boxes each, 128B swizzle) and every 128-row query tile of the item is processed against them.
-//   S = Q K^T : tcgen05.mma  M=128, N=256 + N=16, K=64   (A = Q smem K-major, B = K smem K-major)      -> TMEM cols [0,272)
-//   softmax   : 4 warps, one query row per thread (TMEM lane): pass 1 row max, pass 2 exp2 + row sum; P packed as bf16 pairs
-//               and written back to TENSOR MEMORY (tcgen05.st)                                          -> TMEM cols [272,408)
-//   O = P V   : tcgen05.mma  M=128, N=64, K=272          (A = P in TMEM, B = V smem MN-major)           -> TMEM cols [408,472)
-//   epilogue  : O / rowsum -> bf16 -> global
-// The MMA thread issues PV(n) and then immediately QK(n+1), so the next tile's scores are computed while the softmax warps
-// drain O(n).  The 1-8 query rows that do not fill a 128-row tile (row 256 of a 257-token image) are done by a spare warp on
-// CUDA cores against the K/V already in shared memory.
+// What bounds it: tensor-memory -> register reads run at only ~64 B/clk/SM, so the 128 x 256 fp32 score tile (128 KB) costs
+// ~2000 cycles to read ONCE.  The kernel therefore reads S exactly once (each thread keeps its 128 scores in registers between
+// the max and the exp), and overlaps that read with the tensor-core work of the neighbouring tiles:
+//
+// Persistent CTA per SM; one work item = one (batch, head).  K and V are TMA-loaded once per item in their natural [key][d]
+// layout (two 136-row boxes each, 128B swizzle, double-buffered across items); each 128-row query tile n uses TMEM buffer
+// u = n & 1 (256 columns each):
+//   S = Q K^T : tcgen05.mma M=128, N=256, K=64 (A = Q smem, B = K smem, both K-major)                  -> cols [256u, 256u+256)
+//   softmax   : 8 warps; a query row lives in one TMEM lane, the two warps sharing a lane quarter split its keys
+//               ([0,128) / [128,256)), exchange their partial max / sum through smem, and write P (bf16 pairs) IN PLACE over
+//               the score columns both have already consumed (tcgen05.st)                              -> cols [256u, 256u+128)
+//   O = P V   : tcgen05.mma M=128, N=64, K<=256 (A = P in TMEM, B = V smem MN-major)                   -> cols [256u+128, 256u+192)
+//   epilogue  : (O + tail terms) / rowsum -> bf16 -> global; DEFERRED into the next tile's iteration (between its score read and
+//               its exp), so PV(n) and QK(n+1) run while the softmax warps are busy and nobody waits on the tensor core.
+// Keys 256..Sk-1 (the 257th token of a 257-token image; at most 8) never enter the tensor core: their scores and their
+// rank-1 contribution to O are computed per row on CUDA cores from the K/V rows already in shared memory -- that is what lets
+// a tile fit 256 columns and two tiles fit the 512-column tensor memory.  The 1-8 query rows that do not fill a 128-row tile
+// are done by a spare warp, also on CUDA cores.
 // warps: 0 TMA producer, 1 MMA issuer + TMEM owner, 2-9 softmax/epilogue, 10 leftover rows.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -124,6 +132,7 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
                  "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
+
 __device__ __forceinline__ void tmem_ld_32x32_x16(uint32_t taddr, float (&v)[16]) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -132,59 +141,95 @@ __device__ __forceinline__ void tmem_ld_32x32_x16(uint32_t taddr, float (&v)[16]
                : "r"(taddr) : "memory");
 }
 
+// one MUFU.EX2, no range fix-up (arguments are <= 0 here: s*scale - max*scale; exp2(-inf) = 0)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttnTc {
-  static constexpr int SKP = 272;                        // padded key count (17 x 16)
-  static constexpr int KV_BYTES = SKP * 128;             // 34816 per K or V buffer
+  static constexpr int SKP = 272;                        // rows staged per K / V buffer (17 x 16)
+  static constexpr int NMMA = 256;                       // keys that go through the tensor core
+  static constexpr int MAX_TAIL = 8;                     // keys 256..263 at most on CUDA cores
+  static constexpr int MAX_SK = NMMA + MAX_TAIL;
+  static constexpr int KV_BYTES = SKP * 128;             // 34816
   static constexpr int HALF_ROWS = 136, HALF_BYTES = HALF_ROWS * 128;
   static constexpr int Q_BYTES = 128 * 128;
-  static constexpr int OFF_K = 0, OFF_V = 2 * KV_BYTES, OFF_Q = 4 * KV_BYTES, OFF_P = OFF_Q + 2 * Q_BYTES;   // OFF_P: fp32 scratch of the side warp
-  static constexpr int OFF_X = OFF_P + SKP * 4 + 64;         // partial row max / sum exchange between the two warps of a lane quarter
-  static constexpr int OFF_BAR = OFF_X + 4 * 128 * 4;
+  static constexpr int OFF_K = 0, OFF_V = 2 * KV_BYTES, OFF_Q = 4 * KV_BYTES, OFF_P = OFF_Q + 2 * Q_BYTES;   // OFF_P: fp32 scratch of the spare warp
+  static constexpr int OFF_XMAX = OFF_P + SKP * 4 + 64;          // [2 buf][2 half][128]
+  static constexpr int OFF_XSUM = OFF_XMAX + 2 * 2 * 128 * 4;    // [2 buf][2 half][128]
+  static constexpr int OFF_XTAIL = OFF_XSUM + 2 * 2 * 128 * 4;   // [2 buf][16][128]
+  static constexpr int OFF_BAR = OFF_XTAIL + 2 * MAX_TAIL * 128 * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static constexpr int THREADS = 11 * 32;
-  static constexpr uint32_t COL_S = 0, COL_P = 272, COL_O = 408;
+  static constexpr int TMEM_COLS = 512;
 };
+
+// dot of row ra of one swizzled [row][64] bf16 tile with row rb of another (128B swizzle)
+__device__ __forceinline__ float dot64_swz(const uint8_t* a_tile, int ra, const uint8_t* b_tile, int rb) {
+  float acc = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 x = *reinterpret_cast<const uint4*>(a_tile + ra * 128 + ((c ^ (ra & 7)) << 4));
+    const uint4 y = *reinterpret_cast<const uint4*>(b_tile + rb * 128 + ((c ^ (rb & 7)) << 4));
+    const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&x);
+    const __nv_bfloat162* y2 = reinterpret_cast<const __nv_bfloat162*>(&y);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __bfloat1622float2(x2[e]), fb = __bfloat1622float2(y2[e]);
+      acc = fmaf(fa.x, fb.x, acc); acc = fmaf(fa.y, fb.y, acc);
+    }
+  }
+  return acc;
+}
 
 __global__ void __launch_bounds__(AttnTc::THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-               const bf16* __restrict__ Qg, int ldq, bf16* __restrict__ Og, int ldo, int B, int H, int Sq, int Sk, float scale_log2) {
+               const bf16* __restrict__ Qg, int ldq, bf16* __restrict__ Og, int ldo, int B, int H, int Sq, int Sk, float scale_log2,
+               long long* __restrict__ dbg) {
   using A = AttnTc;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A::OFF_BAR);
-  uint64_t* kv_full = bars;          // [2]
-  uint64_t* kv_empty = bars + 2;     // [2]
+  uint64_t* kv_full = bars;          // [2]  K/V of an item landed
+  uint64_t* kv_empty = bars + 2;     // [2]  MMA commit + 8 softmax warps + spare warp are done with the item's K/V
   uint64_t* q_full = bars + 4;       // [2]
-  uint64_t* q_empty = bars + 6;      // [2]
-  uint64_t* s_full = bars + 8;
-  uint64_t* p_full = bars + 9;
-  uint64_t* o_full = bars + 10;
-  uint64_t* o_empty = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* q_empty = bars + 6;      // [2]  MMA commit (QK done) + 4 tail-scoring warps
+  uint64_t* s_full = bars + 8;       // [2]  per TMEM buffer
+  uint64_t* p_full = bars + 10;      // [2]
+  uint64_t* o_full = bars + 12;      // [2]
+  uint64_t* o_empty = bars + 14;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = B * H;
   const int n_full = Sq / 128, left = Sq % 128;
-  const int n_sub = n_full + (left > 8 ? 1 : 0);          // query tiles done on the tensor cores
+  const int n_sub = n_full + (left > 8 ? 1 : 0);          // query tiles on the tensor cores (host guarantees >= 1)
   const int side_rows = (left > 8) ? 0 : left;            // rows done by the spare warp
   const int side_row0 = n_full * 128;
+  const int n_mma = min(Sk, A::NMMA);
+  const int n_tail = Sk - n_mma;
+  const int pv_steps = (n_mma + 15) / 16;
+  const int my_items = (n_items > static_cast<int>(blockIdx.x)) ? (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
+  const int total = my_items * n_sub;                     // query tiles this CTA processes, in order
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 2);      // MMA commit (last PV of the item) + spare warp
+      mbar_init(&kv_empty[i], 10);
       mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
+      mbar_init(&q_empty[i], 5);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 8);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_empty[i], 8);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 8);
-    mbar_init(o_full, 1);
-    mbar_init(o_empty, 8);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, A::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -193,10 +238,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      int kb = 0; uint32_t kph = 0; int qb = 0; uint32_t qph = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      for (int is = 0; is < my_items; ++is) {
+        const int it = blockIdx.x + is * gridDim.x;
         const int b = it / H, h = it % H;
-        mbar_wait(&kv_empty[kb], kph ^ 1u);
+        const int kb = is & 1;
+        mbar_wait(&kv_empty[kb], ((is >> 1) & 1) ^ 1u);
         mbar_arrive_expect_tx(&kv_full[kb], 2 * A::KV_BYTES);
         uint8_t* sk = smem + A::OFF_K + kb * A::KV_BYTES;
         uint8_t* sv = smem + A::OFF_V + kb * A::KV_BYTES;
@@ -204,229 +250,258 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tma_load_2d(sk + A::HALF_BYTES, &tmK, &kv_full[kb], h * 64, b * Sk + A::HALF_ROWS);
         tma_load_2d(sv, &tmV, &kv_full[kb], h * 64, b * Sk);
         tma_load_2d(sv + A::HALF_BYTES, &tmV, &kv_full[kb], h * 64, b * Sk + A::HALF_ROWS);
-        if (++kb == 2) { kb = 0; kph ^= 1u; }
         for (int t = 0; t < n_sub; ++t) {
-          mbar_wait(&q_empty[qb], qph ^ 1u);
+          const int n = is * n_sub + t, qb = n & 1;
+          mbar_wait(&q_empty[qb], ((n >> 1) & 1) ^ 1u);
           mbar_arrive_expect_tx(&q_full[qb], A::Q_BYTES);
           tma_load_2d(smem + A::OFF_Q + qb * A::Q_BYTES, &tmQ, &q_full[qb], h * 64, b * Sq + t * 128);
-          if (++qb == 2) { qb = 0; qph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer: QK runs one tile ahead of PV =====
     if (lane == 0) {
-      constexpr uint32_t idesc_s256 = make_idesc_bf16_major(128, 256, 0, 0);
-      constexpr uint32_t idesc_s16 = make_idesc_bf16_major(128, 16, 0, 0);
+      constexpr uint32_t idesc_s = make_idesc_bf16_major(128, A::NMMA, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16_major(128, 64, 0, 1);     // B = V, MN-major
-      int kb = 0; uint32_t kph = 0; int qb = 0; uint32_t qph = 0;
-      uint32_t pph = 0, oeph = 0;
-      long long n = 0;                                    // running query-tile counter
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        mbar_wait(&kv_full[kb], kph);
+      auto issue_qk = [&](int n) {
+        const int is = n / n_sub, t = n % n_sub, kb = is & 1, qb = n & 1, u = n & 1;
+        if (t == 0) mbar_wait(&kv_full[kb], (is >> 1) & 1);
+        mbar_wait(&q_full[qb], (n >> 1) & 1);
+        if (n >= 2) mbar_wait(&o_empty[u], ((n >> 1) - 1) & 1);        // the buffer's previous tile has been drained
         tc_fence_after();
+        const uint32_t q_addr = smem_u32(smem + A::OFF_Q + qb * A::Q_BYTES);
         const uint32_t k_addr = smem_u32(smem + A::OFF_K + kb * A::KV_BYTES);
-        const uint32_t v_addr = smem_u32(smem + A::OFF_V + kb * A::KV_BYTES);
-        for (int t = 0; t < n_sub; ++t, ++n) {
-          mbar_wait(&q_full[qb], qph);
-          tc_fence_after();
-          const uint32_t q_addr = smem_u32(smem + A::OFF_Q + qb * A::Q_BYTES);
-          // S = Q K^T   (the S columns were released when p_full of the previous tile was observed below)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = make_desc_sw128(q_addr) + static_cast<uint64_t>(2 * k);
-            umma_bf16(tmem_base + A::COL_S, adesc, make_desc_sw128(k_addr) + static_cast<uint64_t>(2 * k), idesc_s256, k != 0 ? 1u : 0u);
-            umma_bf16(tmem_base + A::COL_S + 256, adesc, make_desc_sw128(k_addr + 256 * 128) + static_cast<uint64_t>(2 * k), idesc_s16, k != 0 ? 1u : 0u);
-          }
-          umma_commit(s_full);
-          umma_commit(&q_empty[qb]);
-          if (++qb == 2) { qb = 0; qph ^= 1u; }
-          // O = P V
-          mbar_wait(p_full, pph); pph ^= 1u;
-          if (n > 0) { mbar_wait(o_empty, oeph); oeph ^= 1u; }
-          tc_fence_after();
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + static_cast<uint32_t>(256 * u), make_desc_sw128(q_addr) + static_cast<uint64_t>(2 * k),
+                    make_desc_sw128(k_addr) + static_cast<uint64_t>(2 * k), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[u]);
+        umma_commit(&q_empty[qb]);
+      };
+      if (total > 0) issue_qk(0);
+      for (int n = 0; n < total; ++n) {
+        if (n + 1 < total) issue_qk(n + 1);
+        const int is = n / n_sub, t = n % n_sub, kb = is & 1, u = n & 1;
+        mbar_wait(&p_full[u], (n >> 1) & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(smem + A::OFF_V + kb * A::KV_BYTES);
 #pragma unroll 1
-          for (int k = 0; k < A::SKP / 16; ++k)
-            umma_bf16_ts(tmem_base + A::COL_O, tmem_base + A::COL_P + static_cast<uint32_t>(8 * k),
-                         make_desc(v_addr + static_cast<uint32_t>(k) * 2048u, 1024u, 1024u), idesc_pv, k != 0 ? 1u : 0u);
-          umma_commit(o_full);
-          if (t == n_sub - 1) umma_commit(&kv_empty[kb]);
-        }
-        if (n_sub == 0) mbar_arrive(&kv_empty[kb]);
-        if (++kb == 2) { kb = 0; kph ^= 1u; }
+        for (int k = 0; k < pv_steps; ++k)
+          umma_bf16_ts(tmem_base + static_cast<uint32_t>(256 * u + 128), tmem_base + static_cast<uint32_t>(256 * u + 8 * k),
+                       make_desc(v_addr + static_cast<uint32_t>(k) * 2048u, 1024u, 1024u), idesc_pv, k != 0 ? 1u : 0u);
+        umma_commit(&o_full[u]);
+        if (t == n_sub - 1) umma_commit(&kv_empty[kb]);
       }
     }
   } else if (warp < 10) {
-    // ===== softmax + epilogue: 8 warps.  A query row lives in one TMEM lane; the two warps that share a lane quarter split the
-    //       row's key columns (half 0: keys [0,128), half 1: keys [128,272)) and exchange their partial max / sum through smem.
-    const int lane_grp = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int rloc = lane_grp * 32 + lane;                                 // row inside the 128-row tile
-    const uint32_t lane_off = static_cast<uint32_t>(lane_grp * 32) << 16;
-    float* xmax = reinterpret_cast<float*>(smem + A::OFF_X);               // [2][128]
-    float* xsum = xmax + 256;                                              // [2][128]
-    const int c_begin = half * 4, c_end = c_begin + 4;                     // 32-key chunks of this half (the 16-key tail belongs to half 1)
-    uint32_t sph = 0, oph = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    // ===== softmax + (deferred) epilogue =====
+    const int qd = warp & 3;                               // TMEM lane quarter
+    const int hf = (warp - 2) >> 2;                        // which half of the keys / of the O columns
+    const int rloc = qd * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    float* xmax = reinterpret_cast<float*>(smem + A::OFF_XMAX);
+    float* xsum = reinterpret_cast<float*>(smem + A::OFF_XSUM);
+    float* xtail = reinterpret_cast<float*>(smem + A::OFF_XTAIL);
+#ifdef DEER_ATTN_PROF
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool prof = (dbg != nullptr) && warp == 2 && lane == 0;
+#define TICK(i) do { if (prof) { const long long _t = clock64(); tacc[i] += _t - t0; t0 = _t; } } while (0)
+    long long t0 = prof ? clock64() : 0;
+#else
+#define TICK(i) do { } while (0)
+#endif
+
+    // epilogue of tile n (buffer u): (O + tail keys) / l -> global.  Both warps of a quarter have passed a bar.sync since the
+    // partner published xsum / xtail for tile n.
+    auto epilogue = [&](int n) {
+      const int is = n / n_sub, t = n % n_sub, kb = is & 1, u = n & 1;
+      const int it = blockIdx.x + is * gridDim.x;
       const int b = it / H, h = it % H;
-      for (int t = 0; t < n_sub; ++t) {
-        mbar_wait(s_full, sph); sph ^= 1u;
-        tc_fence_after();
-        const uint32_t ts = tmem_base + lane_off + A::COL_S;
-        // ---- pass 1: partial row max (TMEM loads software-pipelined: the next chunk is in flight while this one is reduced)
-        float m = -INFINITY;
-        float va[32], vb[32];
-        tmem_ld_32x32(ts + static_cast<uint32_t>(c_begin * 32), va);
+      mbar_wait(&o_full[u], (n >> 1) & 1);
+      tc_fence_after();
+      TICK(5);
+      const float inv = 1.0f / (xsum[(u * 2 + 0) * 128 + rloc] + xsum[(u * 2 + 1) * 128 + rloc]);
+      const uint8_t* sv = smem + A::OFF_V + kb * A::KV_BYTES;
+      const int row = t * 128 + rloc;
+      bf16* orow = Og + (static_cast<size_t>(b) * Sq + row) * ldo + h * 64 + hf * 32;
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {                     // 16 O columns at a time (keeps the register peak down)
+        float v[16];
+        tmem_ld_32x32_x16(tmem_base + lane_off + static_cast<uint32_t>(256 * u + 128 + hf * 32 + hh * 16), v);
         tmem_ld_wait();
+        for (int j = 0; j < n_tail; ++j) {
+          const int kr = A::NMMA + j;
+          const float pj = xtail[(u * A::MAX_TAIL + j) * 128 + rloc];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c = c_begin + cc;
-          float (&cur)[32] = (cc & 1) ? vb : va;
-          float (&nxt)[32] = (cc & 1) ? va : vb;
-          if (cc < 3) tmem_ld_32x32(ts + static_cast<uint32_t>((c + 1) * 32), nxt);
-          if (c * 32 + 32 <= Sk) {
+          for (int cc = 0; cc < 2; ++cc) {                 // two 16-byte chunks = 16 d; every lane reads the same address (broadcast)
+            const uint4 y = *reinterpret_cast<const uint4*>(sv + kr * 128 + (((hf * 4 + hh * 2 + cc) ^ (kr & 7)) << 4));
+            const __nv_bfloat162* y2 = reinterpret_cast<const __nv_bfloat162*>(&y);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) m = fmaxf(m, cur[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (c * 32 + j < Sk) m = fmaxf(m, cur[j]);
-          }
-          if (cc < 3) tmem_ld_wait();
-        }
-        float vt[16];
-        if (half == 1) {
-          tmem_ld_32x32_x16(ts + 256u, vt);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) if (256 + j < Sk) m = fmaxf(m, vt[j]);
-        }
-        xmax[half * 128 + rloc] = m;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + lane_grp) : "memory");
-        m = fmaxf(m, xmax[(half ^ 1) * 128 + rloc]);
-        const float ms = m * scale_log2;
-        // ---- pass 2: p = exp2(s*scale - m*scale), partial row sum, bf16 pairs -> TMEM
-        float l = 0.0f;
-        const uint32_t tp = tmem_base + lane_off + A::COL_P;
-        tmem_ld_32x32(ts + static_cast<uint32_t>(c_begin * 32), va);
-        tmem_ld_wait();
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c = c_begin + cc;
-          float (&cur)[32] = (cc & 1) ? vb : va;
-          float (&nxt)[32] = (cc & 1) ? va : vb;
-          if (cc < 3) tmem_ld_32x32(ts + static_cast<uint32_t>((c + 1) * 32), nxt);
-          uint32_t pk[16];
-          if (c * 32 + 32 <= Sk) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float p0 = exp2f(fmaf(cur[j], scale_log2, -ms)), p1 = exp2f(fmaf(cur[j + 1], scale_log2, -ms));
-              l += p0 + p1;
-              pk[j >> 1] = pack_bf16x2(p0, p1);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float p0 = (c * 32 + j < Sk) ? exp2f(fmaf(cur[j], scale_log2, -ms)) : 0.0f;
-              const float p1 = (c * 32 + j + 1 < Sk) ? exp2f(fmaf(cur[j + 1], scale_log2, -ms)) : 0.0f;
-              l += p0 + p1;
-              pk[j >> 1] = pack_bf16x2(p0, p1);
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(y2[e]);
+              v[cc * 8 + 2 * e] = fmaf(pj, f.x, v[cc * 8 + 2 * e]);
+              v[cc * 8 + 2 * e + 1] = fmaf(pj, f.y, v[cc * 8 + 2 * e + 1]);
             }
           }
-          tmem_st_32x32b_x16(tp + static_cast<uint32_t>(c * 16), pk);
-          if (cc < 3) tmem_ld_wait();
         }
-        if (half == 1) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            const float p0 = (256 + j < Sk) ? exp2f(fmaf(vt[j], scale_log2, -ms)) : 0.0f;
-            const float p1 = (256 + j + 1 < Sk) ? exp2f(fmaf(vt[j + 1], scale_log2, -ms)) : 0.0f;
-            l += p0 + p1;
-            pk[j >> 1] = pack_bf16x2(p0, p1);
-          }
-          tmem_st_32x32b_x8(tp + 128u, pk);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        xsum[half * 128 + rloc] = l;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
-        // ---- epilogue: this warp drains O columns [32*half, 32*half+32) of its rows
-        mbar_wait(o_full, oph); oph ^= 1u;
-        tc_fence_after();
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + lane_grp) : "memory");      // partner's partial sum is visible
-        const float inv = 1.0f / (l + xsum[(half ^ 1) * 128 + rloc]);
-        const int row = t * 128 + rloc;
-        bf16* orow = Og + (static_cast<size_t>(b) * Sq + row) * ldo + h * 64 + half * 32;
-        float v[32];
-        tmem_ld_32x32(tmem_base + lane_off + A::COL_O + static_cast<uint32_t>(half * 32), v);
-        tmem_ld_wait();
         if (row < Sq) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
+          for (int j = 0; j < 16; j += 8) {
             uint4 o;
             o.x = pack_bf16x2(v[j] * inv, v[j + 1] * inv); o.y = pack_bf16x2(v[j + 2] * inv, v[j + 3] * inv);
             o.z = pack_bf16x2(v[j + 4] * inv, v[j + 5] * inv); o.w = pack_bf16x2(v[j + 6] * inv, v[j + 7] * inv);
-            *reinterpret_cast<uint4*>(orow + j) = o;
+            *reinterpret_cast<uint4*>(orow + hh * 16 + j) = o;
           }
         }
-        tc_fence_before();
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + lane_grp) : "memory");      // both halves done with xmax/xsum before they are rewritten
-        if (lane == 0) mbar_arrive(o_empty);
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&o_empty[u]);
+        if (t == n_sub - 1) mbar_arrive(&kv_empty[kb]);
+      }
+    };
+
+    for (int n = 0; n <= total; ++n) {
+      if (n == total) {                                    // drain: only the last tile's epilogue is left
+        if (total > 0) {
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+          epilogue(total - 1);
+        }
+        break;
+      }
+      const int is = n / n_sub, kb = is & 1, qb = n & 1, u = n & 1;
+      mbar_wait(&s_full[u], (n >> 1) & 1);
+      tc_fence_after();
+      TICK(0);
+      // ---- this thread's 128 scores, read ONCE
+      const uint32_t ts = tmem_base + lane_off + static_cast<uint32_t>(256 * u + 128 * hf);
+      float s0[32], s1[32], s2[32], s3[32];
+      tmem_ld_32x32(ts, s0);
+      tmem_ld_32x32(ts + 32u, s1);
+      tmem_ld_32x32(ts + 64u, s2);
+      tmem_ld_32x32(ts + 96u, s3);
+      // tail keys (>= 256) on CUDA cores while the loads are in flight: this row's q (smem) . staged K rows
+      float m = -INFINITY;
+      if (hf == 1) {
+        const uint8_t* sq = smem + A::OFF_Q + qb * A::Q_BYTES;
+        const uint8_t* sk = smem + A::OFF_K + kb * A::KV_BYTES;
+#pragma unroll 1
+        for (int j = 0; j < n_tail; ++j) {                 // raw scores parked in smem (each thread reads back only its own slot)
+          const float sj = dot64_swz(sq, rloc, sk, A::NMMA + j);
+          xtail[(u * A::MAX_TAIL + j) * 128 + rloc] = sj;
+          m = fmaxf(m, sj);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&q_empty[qb]);
+      }
+      tmem_ld_wait();
+      TICK(6);
+      const int c0 = 128 * hf;
+      if (c0 + 128 > n_mma) {                              // keys past n_mma (padding / next image's rows): score -inf -> p = 0
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (c0 + j >= n_mma) s0[j] = -INFINITY;
+          if (c0 + 32 + j >= n_mma) s1[j] = -INFINITY;
+          if (c0 + 64 + j >= n_mma) s2[j] = -INFINITY;
+          if (c0 + 96 + j >= n_mma) s3[j] = -INFINITY;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) m = fmaxf(fmaxf(m, s0[j]), fmaxf(fmaxf(s1[j], s2[j]), s3[j]));
+      xmax[(u * 2 + hf) * 128 + rloc] = m;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");     // partner's max is visible AND both halves of S have been read
+      m = fmaxf(m, xmax[(u * 2 + (hf ^ 1)) * 128 + rloc]);
+      const float ms = m * scale_log2;
+      TICK(1);
+      // ---- the previous tile's epilogue goes here: its PV finished while we were reading scores
+      if (n > 0) epilogue(n - 1);
+      TICK(2);
+      // ---- p = exp2(s*scale - m*scale), partial row sum; bf16 pairs written in place over the consumed score columns
+      float l = 0.0f;
+      const uint32_t tp = tmem_base + lane_off + static_cast<uint32_t>(256 * u + 64 * hf);
+#define SOFTMAX_CHUNK(SX, CI)                                                                                          \
+      {                                                                                                                 \
+        uint32_t pk[16];                                                                                                \
+        _Pragma("unroll") for (int j = 0; j < 32; j += 2) {                                                             \
+          const float p0 = ex2_approx(fmaf(SX[j], scale_log2, -ms)), p1 = ex2_approx(fmaf(SX[j + 1], scale_log2, -ms)); \
+          l += p0 + p1;                                                                                                 \
+          pk[j >> 1] = pack_bf16x2(p0, p1);                                                                             \
+        }                                                                                                               \
+        tmem_st_32x32b_x16(tp + static_cast<uint32_t>((CI) * 16), pk);                                                  \
+      }
+      SOFTMAX_CHUNK(s0, 0)
+      SOFTMAX_CHUNK(s1, 1)
+      SOFTMAX_CHUNK(s2, 2)
+      SOFTMAX_CHUNK(s3, 3)
+#undef SOFTMAX_CHUNK
+      if (hf == 1) {
+#pragma unroll 1
+        for (int j = 0; j < n_tail; ++j) {
+          const float pj = ex2_approx(fmaf(xtail[(u * A::MAX_TAIL + j) * 128 + rloc], scale_log2, -ms));
+          l += pj;
+          xtail[(u * A::MAX_TAIL + j) * 128 + rloc] = pj;
+        }
+      }
+      xsum[(u * 2 + hf) * 128 + rloc] = l;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[u]);
+      TICK(3);
     }
+    TICK(4);
+#ifdef DEER_ATTN_PROF
+    if (prof) for (int i = 0; i < 8; ++i) dbg[blockIdx.x * 8 + i] = tacc[i];
+#endif
+#undef TICK
   } else {
     // ===== spare warp: the few query rows that do not fill a 128-row tile, on CUDA cores, against the smem K/V =====
-    int kb = 0; uint32_t kph = 0;
     float* pbuf = reinterpret_cast<float*>(smem + A::OFF_P);
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const int b = it / H, h = it % H;
-      mbar_wait(&kv_full[kb], kph);
-      const uint8_t* sk = smem + A::OFF_K + kb * A::KV_BYTES;
-      const uint8_t* sv = smem + A::OFF_V + kb * A::KV_BYTES;
+    for (int is = 0; is < my_items; ++is) {
+      const int it = blockIdx.x + is * gridDim.x;
+      const int b = it / H, h = it % H, kb = is & 1;
+      mbar_wait(&kv_full[kb], (is >> 1) & 1);
+      const uint8_t* sK = smem + A::OFF_K + kb * A::KV_BYTES;
+      const uint8_t* sV = smem + A::OFF_V + kb * A::KV_BYTES;
       for (int r = 0; r < side_rows; ++r) {
         const int row = side_row0 + r;
         const uint4* qp = reinterpret_cast<const uint4*>(Qg + (static_cast<size_t>(b) * Sq + row) * ldq + h * 64);
         uint4 q[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) q[c] = __ldg(qp + c);
-        float sc[9];
         float m = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          const int j = lane + 32 * i;
+#pragma unroll 1
+        for (int j = lane; j < Sk; j += 32) {              // rolled on purpose: this rarely-run path must stay small in the I-cache
           float acc = 0.0f;
-          if (j < Sk) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint4 kk = *reinterpret_cast<const uint4*>(sk + j * 128 + ((c ^ (j & 7)) << 4));
-              const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&q[c]);
-              const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&kk);
+          for (int c = 0; c < 8; ++c) {
+            const uint4 kk = *reinterpret_cast<const uint4*>(sK + j * 128 + ((c ^ (j & 7)) << 4));
+            const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&q[c]);
+            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&kk);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
-                acc = fmaf(fa.x, fb.x, acc); acc = fmaf(fa.y, fb.y, acc);
-              }
+            for (int e = 0; e < 4; ++e) {
+              const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
+              acc = fmaf(fa.x, fb.x, acc); acc = fmaf(fa.y, fb.y, acc);
             }
-            acc *= scale_log2;
-            m = fmaxf(m, acc);
-          } else acc = -INFINITY;
-          sc[i] = acc;
+          }
+          acc *= scale_log2;
+          pbuf[j] = acc;
+          m = fmaxf(m, acc);
         }
         m = warp_max(m);
         float l = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          const int j = lane + 32 * i;
-          const float p = (j < Sk) ? exp2f(sc[i] - m) : 0.0f;
+#pragma unroll 1
+        for (int j = lane; j < Sk; j += 32) {
+          const float p = ex2_approx(pbuf[j] - m);
+          pbuf[j] = p;
           l += p;
-          if (j < A::SKP) pbuf[j] = p;
         }
         l = warp_sum(l);
         __syncwarp();
         float o0 = 0.0f, o1 = 0.0f;                        // lane owns d = 2*lane, 2*lane+1
         for (int j = 0; j < Sk; ++j) {
-          const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(sv + j * 128 + (((lane >> 2) ^ (j & 7)) << 4) + (lane & 3) * 4);
+          const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(sV + j * 128 + (((lane >> 2) ^ (j & 7)) << 4) + (lane & 3) * 4);
           const float2 f = __bfloat1622float2(vv);
           const float p = pbuf[j];
           o0 = fmaf(p, f.x, o0); o1 = fmaf(p, f.y, o1);
@@ -437,13 +512,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&kv_empty[kb]);
-      if (++kb == 2) { kb = 0; kph ^= 1u; }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, A::TMEM_COLS);
   }
 }

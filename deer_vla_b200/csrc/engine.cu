@@ -175,6 +175,7 @@ static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int
 }
 
 static std::map<TmapKey, CUtensorMap> g_attn_tmaps;
+static long long* g_attn_dbg = nullptr;       // optional per-CTA phase-cycle counters (deer_attn_debug)
 static const CUtensorMap* attn_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box) {
   TmapKey k{ptr, rows, cols, ld, box};
   auto it = g_attn_tmaps.find(k);
@@ -194,7 +195,7 @@ static int run_attention(int impl, int dtype, const AttnParams& p, std::string* 
   const bool plain = dtype == 0 && p.hd == 64 && !p.causal && !p.alibi_slopes && !p.kv_len && !p.qmode && !p.n_dev && p.ldk == p.ldv;
   static const bool no_tc = getenv("DEER_ATTN_NO_TC") != nullptr;
   bool done = false;
-  if (impl == 0 && plain && !no_tc && p.Sk <= AttnTc::SKP && (p.ldq % 8) == 0 && (p.ldk % 8) == 0 && (p.ldo % 8) == 0) {
+  if (impl == 0 && plain && !no_tc && p.Sk <= AttnTc::MAX_SK && p.Sq > 8 && (p.ldq % 8) == 0 && (p.ldk % 8) == 0 && (p.ldo % 8) == 0) {
     const uint64_t width = (uint64_t)p.H * 64;
     const CUtensorMap* tq = attn_tmap(p.Q, (uint64_t)p.B_host * p.Sq, width, p.ldq, 128);
     const CUtensorMap* tk = attn_tmap(p.K, (uint64_t)p.B_host * p.Sk, width, p.ldk, AttnTc::HALF_ROWS);
@@ -208,7 +209,7 @@ static int run_attention(int impl, int dtype, const AttnParams& p, std::string* 
       const int grid = std::min(p.B_host * p.H, DEER_NUM_SMS);
       attn_tc_kernel<<<grid, AttnTc::THREADS, AttnTc::SMEM_BYTES, st>>>(*tq, *tk, *tv, reinterpret_cast<const bf16*>(p.Q), p.ldq,
                                                                         reinterpret_cast<bf16*>(p.O), p.ldo, p.B_host, p.H, p.Sq, p.Sk,
-                                                                        p.scale * 1.4426950408889634f);
+                                                                        p.scale * 1.4426950408889634f, g_attn_dbg);
       done = true;
     }
   }
@@ -1257,5 +1258,13 @@ extern "C" int deer_op_pv_probe(const void* P, const void* V, float* O, int K, i
                                                                            (uint32_t)sbo_bytes, (uint32_t)kstep_bytes);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_err(nullptr, DEER_E_CUDA, "pv probe launch failed: %s", cudaGetErrorString(e));
+  return DEER_OK;
+}
+
+// tuning aid: enable / read per-CTA cycle counters of the attention kernel's softmax warp (5 phases x up to 512 CTAs)
+extern "C" int deer_attn_debug(int enable, long long* host_out, int n) {
+  if (enable && !g_attn_dbg) { cudaMalloc(reinterpret_cast<void**>(&g_attn_dbg), 512 * 8 * sizeof(long long)); cudaMemset(g_attn_dbg, 0, 512 * 8 * sizeof(long long)); }
+  if (host_out && g_attn_dbg) { cudaDeviceSynchronize(); cudaMemcpy(host_out, g_attn_dbg, std::min(n, 512 * 8) * sizeof(long long), cudaMemcpyDeviceToHost); }
+  if (!enable && g_attn_dbg) { cudaFree(g_attn_dbg); g_attn_dbg = nullptr; }
   return DEER_OK;
 }

@@ -41,25 +41,27 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the thread SLEEPS in hardware until the phase flips or ~the hint (ns) expires, instead
+// of spinning.  (Without the hint the single-thread TMA / MMA roles' spin loops issued as many instructions as the math
+// warps sharing their scheduler -- visible as TRYWAIT/BRA/YIELD in the ncu instruction mix.)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a launch failure (trap), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
+    if (++spins > (1u << 24)) __trap();            // >> seconds: each failed try sleeps up to ~20 us
   }
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {

@@ -190,6 +190,9 @@ int deer_op_attention(int impl, int dtype, const void* Q, int ldq, const void* K
  * tensor memory (tcgen05.st) as the A operand and V read in its natural [key][d] layout as an MN-major B operand. */
 int deer_op_pv_probe(const void* P, const void* V, float* O, int K, int lbo_bytes, int sbo_bytes, int kstep_bytes, void* stream);
 
+/* tuning aid: per-CTA cycle counters of the attention kernel's softmax warp (wait-S, pass 1, pass 2, wait-O, epilogue). */
+int deer_attn_debug(int enable, long long* host_out, int n);
+
 #ifdef __cplusplus
 }
 #endif

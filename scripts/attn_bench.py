@@ -25,3 +25,13 @@ for name, impl in (("tcgen05", 0), ("mma.sync flash", 3)):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     print(f"{name:16s} {ms:7.3f} ms  {4 * B * H * S * S * 64 / ms / 1e9:7.1f} TFLOP/s")
+
+import numpy as np
+lib.deer_attn_debug(1, None, 0)
+rc = lib.deer_op_attention(0, 0, C.c_void_p(p), 3 * W, C.c_void_p(p + 2 * W), C.c_void_p(p + 4 * W), 3 * W, C.c_void_p(out.data_ptr()), W, B, H, S, S, 64, 0.125, C.c_void_p(st))
+buf = np.zeros(512 * 8, dtype=np.int64)
+lib.deer_attn_debug(1, buf.ctypes.data_as(C.c_void_p), buf.size)
+d = buf.reshape(512, 8)[:148, :8]
+tiles = 2 * (B * H) / 148
+m = d.mean(0) / tiles
+print("cycles per tile (softmax warp 2): wait_S %.0f | S loads issued->landed %.0f, max+exchange %.0f | epilogue: wait_O %.0f, rest %.0f | exp+P-store %.0f | total %.0f" % (m[0], m[6], m[1], m[5], m[2], m[3], d.sum(1).mean() / tiles))
