@@ -146,7 +146,7 @@ def engine_arm(a):
     max_layer, exit_ratio, desc = WORKLOADS[a.workload]
     cfg = config_3b(max_layer)
     B, S = a.batch, a.seq
-    eng = DeerEngine(cfg, max_batch=B, max_slots=B, max_seq=S, device=local, precision="bf16", gemm_impl="tcgen05")
+    eng = DeerEngine(cfg, max_batch=B, max_slots=B, max_seq=S, device=local, precision="bf16", gemm_impl="tcgen05", use_graph=a.graph)
     t0 = time.time()
     eng.load_state_dict(synth_state_dict(cfg, 0))
     t_load = time.time() - t0
@@ -295,7 +295,8 @@ def engine_arm(a):
                 "config": {"workload": desc, "episodes_per_gpu": B, "seq_len": S, "max_layer": max_layer, "exit_ratio": exit_ratio,
                            "parallelism": f"episode-sharded replicas x{world}", "thresholds": thresholds,
                            "l2": "each step reads a different 270 MB frame set (> 126 MB L2); weights 3.1 GB",
-                           "weights": "seeded synthetic (no checkpoints offline)", "calibration_samples": int(table.shape[1])},
+                           "weights": "seeded synthetic (no checkpoints offline)", "calibration_samples": int(table.shape[1]),
+                           "cuda_graph": bool(a.graph)},
                 "e2e": {"value": e2e_value, "unit": "action-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
                 "exit_histogram": {str(e): int(exit_hist[e]) for e in exits_sorted},
@@ -320,6 +321,7 @@ def main():
     ap.add_argument("--calib-steps", type=int, default=8)
     ap.add_argument("--cpu-steps", type=int, default=8, help="batch-1 oracle steps timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay each step as one CUDA graph with conditional exit nodes (latency mode)")
     a = ap.parse_args()
     if a.impl == "reference":
         reference_arm(a)

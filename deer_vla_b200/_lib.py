@@ -27,7 +27,7 @@ class DeerCConfig(C.Structure):
         "xattn_heads", "xattn_dim_head", "xattn_ff_mult", "media_token_id",
         "n_layers", "exit_interval", "max_layer", "is_mpt_9b",
         "lstm_hidden", "lstm_layers", "mlp_dim0", "mlp_dim1", "threshold_type", "steps_per_stage",
-        "max_batch", "max_slots", "max_seq", "precision", "gemm_impl", "debug_taps", "host_control")]
+        "max_batch", "max_slots", "max_seq", "precision", "gemm_impl", "debug_taps", "host_control", "use_graph")]
 
 
 class DeerStats(C.Structure):

@@ -307,6 +307,12 @@ struct deer_ctx {
   int* nact_hist = nullptr;            // device [16]: active count after each probe of the last step
   int n_probes_last = 0, n_last = 0;
   cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
+  // CUDA-graph mode
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; cudaGraph_t graph = nullptr; int seen = 0; int64_t launches = 0, gemms = 0; double flops = 0; int probes = 0; };
+  std::map<std::tuple<int, int, int, unsigned, int>, GraphEntry> graphs;
+  cudaStream_t cap_streams[20] = {nullptr};
+  int cap_level = -1;                 // >= 0 while a step is being captured
+  int64_t graph_launches = 0, graphs_built = 0;
   GemmCtx gemm;
   LaunchStats stats;
   int64_t steps = 0;
@@ -570,6 +576,8 @@ extern "C" void deer_destroy(deer_ctx* c) {
   if (c->ev_step0) cudaEventDestroy(c->ev_step0);
   if (c->ev_step1) cudaEventDestroy(c->ev_step1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  for (auto& kv : c->graphs) { if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec); if (kv.second.graph) cudaGraphDestroy(kv.second.graph); }
+  for (auto s2 : c->cap_streams) if (s2) cudaStreamDestroy(s2);
   delete c;
 }
 
@@ -1010,7 +1018,7 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
   if (!exit_out) exit_out = c->o_exit;
   if (!delta_out) delta_out = c->o_delta;
   c->tap_n = n; c->tap_S = S;
-  init_episodes_kernel<<<(n + 127) / 128, 128, 0, st>>>(c->meta[0], c->n_active, slots, ids, mask, timesteps, n, S, f.media_token_id,
+  init_episodes_kernel<<<(n + 127) / 128, 128, 0, s.st>>>(c->meta[0], c->n_active, slots, ids, mask, timesteps, n, S, f.media_token_id,
                                                           f.steps_per_stage, c->n_thr, exit_out, delta_out);
   KLAUNCH_CHECK("init_episodes");
   c->n_probes_last = 0; c->n_last = n;
@@ -1019,13 +1027,13 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
     for (auto& r : c->gemm.recs) { c->gemm.pool.push_back(r.e0); c->gemm.pool.push_back(r.e1); }
     c->gemm.recs.clear();
     if (!c->ev_step0) { cudaEventCreate(&c->ev_step0); cudaEventCreate(&c->ev_step1); }
-    cudaEventRecord(c->ev_step0, st);
+    cudaEventRecord(c->ev_step0, s.st);
   }
   c->gemm.tag = 0;
   RET(s.vision(rgb, grip));
   c->gemm.tag = 2;
-  if (c->dtype == 1) embed_kernel<float><<<n * S, 256, 0, st>>>(ids, reinterpret_cast<const float*>(c->wte), c->x[0], n * S, f.d_model, f.vocab);
-  else embed_kernel<bf16><<<n * S, 256, 0, st>>>(ids, reinterpret_cast<const bf16*>(c->wte), c->x[0], n * S, f.d_model, f.vocab);
+  if (c->dtype == 1) embed_kernel<float><<<n * S, 256, 0, s.st>>>(ids, reinterpret_cast<const float*>(c->wte), c->x[0], n * S, f.d_model, f.vocab);
+  else embed_kernel<bf16><<<n * S, 256, 0, s.st>>>(ids, reinterpret_cast<const bf16*>(c->wte), c->x[0], n * S, f.d_model, f.vocab);
   KLAUNCH_CHECK("embed");
   const int last_layer = (static_exit >= 0) ? static_exit : c->ctrl_max_layer;
   const int first_exit = c->exits[0];
@@ -1041,7 +1049,7 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
       if (li == first_exit - 1) {
         // first exit compares with the head applied to the PREVIOUS layer's features (value_net.py:122-125)
         RET(s.head_eval());
-        copy_pose_kernel<<<(n * 6 + 127) / 128, 128, 0, st>>>(c->cur_pose, c->meta[s.cur].prev_pose, n, s.nact());
+        copy_pose_kernel<<<(n * 6 + 127) / 128, 128, 0, s.st>>>(c->cur_pose, c->meta[s.cur].prev_pose, n, s.nact());
         KLAUNCH_CHECK("copy_pose");
       }
     }
@@ -1056,28 +1064,54 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
     g.pose_out = pose_out; g.grip_out = grip_out; g.action_out = action_out; g.exit_out = exit_out; g.delta_out = delta_out;
     g.exit_flag = c->exit_flag; g.src_of_new = c->src_of_new;
     const int nxt = s.cur ^ 1;
-    exit_gate_kernel<<<1, 1024, 0, st>>>(g, c->meta[s.cur], c->n_active + s.cur, c->n_active + nxt,
-                                         c->nact_hist + std::min(c->n_probes_last, 15));
+    // graph capture: the layers after this exit go into a conditional IF node; the gate kernel sets its condition
+    const bool wrap_cond = (c->cap_level >= 0) && !g.forced;
+    if (wrap_cond) {
+      cudaStreamCaptureStatus cst; unsigned long long cid; cudaGraph_t cg; const cudaGraphNode_t* deps; size_t nd;
+      CK(cudaStreamGetCaptureInfo_v2(s.st, &cst, &cid, &cg, &deps, &nd));
+      CK(cudaGraphConditionalHandleCreate(&g.cond, cg, 0, cudaGraphCondAssignDefault));
+      g.has_cond = 1;
+    }
+    exit_gate_kernel<<<1, 1024, 0, s.st>>>(g, c->meta[s.cur], c->n_active + s.cur, c->n_active + nxt,
+                                           c->nact_hist + std::min(c->n_probes_last, 15));
     KLAUNCH_CHECK("exit_gate");
     c->n_probes_last++;
     c->gemm.epoch = c->n_probes_last;
-    commit_state_kernel<<<dim3(n, f.lstm_layers), 256, 0, st>>>(c->exit_flag, c->meta[s.cur].slot, c->cand_h, c->cand_c, c->h_state, c->c_state,
+    commit_state_kernel<<<dim3(n, f.lstm_layers), 256, 0, s.st>>>(c->exit_flag, c->meta[s.cur].slot, c->cand_h, c->cand_c, c->h_state, c->c_state,
                                                                f.lstm_layers, f.lstm_hidden, f.max_batch, n, c->n_active + s.cur);
     KLAUNCH_CHECK("commit_state");
     if (g.forced) break;
-    compact_kernel<T><<<dim3(n, 8), 256, 0, st>>>(c->src_of_new, c->x[s.cur], c->x[nxt], (size_t)S * f.d_model, s.tp(c->media[s.cur]), s.tp(c->media[nxt]),
+    compact_kernel<T><<<dim3(n, 8), 256, 0, s.st>>>(c->src_of_new, c->x[s.cur], c->x[nxt], (size_t)S * f.d_model, s.tp(c->media[s.cur]), s.tp(c->media[nxt]),
                                                   (size_t)2 * c->nl * f.vit_width, c->meta[s.cur], c->meta[nxt], c->cur_pose, S, n, c->n_active + nxt);
     KLAUNCH_CHECK("compact");
     s.cur = nxt;
+    if (wrap_cond) {
+      cudaStreamCaptureStatus cst; unsigned long long cid; cudaGraph_t cg; const cudaGraphNode_t* deps; size_t nd;
+      CK(cudaStreamGetCaptureInfo_v2(s.st, &cst, &cid, &cg, &deps, &nd));
+      cudaGraphNodeParams np = {};
+      np.type = cudaGraphNodeTypeConditional;
+      np.conditional.handle = g.cond;
+      np.conditional.type = cudaGraphCondTypeIf;
+      np.conditional.size = 1;
+      cudaGraphNode_t cnode;
+      CK(cudaGraphAddNode(&cnode, cg, deps, nd, &np));
+      CK(cudaStreamUpdateCaptureDependencies(s.st, &cnode, 1, cudaStreamSetCaptureDependencies));
+      cudaGraph_t body = np.conditional.phGraph_out[0];
+      c->cap_level++;
+      if (c->cap_level >= 19) return set_err(&c->err, DEER_E_INVALID, "too many nested exits for graph capture");
+      if (!c->cap_streams[c->cap_level]) CK(cudaStreamCreateWithFlags(&c->cap_streams[c->cap_level], cudaStreamNonBlocking));
+      CK(cudaStreamBeginCaptureToGraph(c->cap_streams[c->cap_level], body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+      s.st = c->cap_streams[c->cap_level];
+    }
     if (f.host_control) {
       // the reference's per-probe device->host sync (value_net.py:293): stop LAUNCHING once every episode has exited
-      CK(cudaMemcpyAsync(c->h_nact, c->n_active + s.cur, 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
+      CK(cudaMemcpyAsync(c->h_nact, c->n_active + s.cur, 4, cudaMemcpyDeviceToHost, s.st));
+      CK(cudaStreamSynchronize(s.st));
       if (*c->h_nact == 0) break;
       s.n = *c->h_nact;                       // exact-sized launches from here on
     }
   }
-  if (c->gemm.profile) cudaEventRecord(c->ev_step1, st);
+  if (c->gemm.profile) cudaEventRecord(c->ev_step1, s.st);
   return DEER_OK;
 }
 
@@ -1092,6 +1126,74 @@ static int validate_step(deer_ctx* c, int n, int S, int static_exit, uint32_t fl
   return DEER_OK;
 }
 
+static int step_dispatch(deer_ctx* c, int n, const int32_t* slots, const float* rgb, const float* gripper, const int64_t* ids,
+                         const uint8_t* mask, int S, const int32_t* timesteps, int static_exit, uint32_t flags, float* pose_out,
+                         float* gripper_out, float* action_out, int32_t* exit_out, float* delta_out, cudaStream_t st) {
+  if (c->dtype == 1)
+    return step_impl<float>(c, n, slots, rgb, gripper, ids, mask, S, timesteps, static_exit, flags, pose_out, gripper_out, action_out, exit_out, delta_out, st);
+  return step_impl<bf16>(c, n, slots, rgb, gripper, ids, mask, S, timesteps, static_exit, flags, pose_out, gripper_out, action_out, exit_out, delta_out, st);
+}
+
+// CUDA-graph mode: inputs are staged into engine-owned buffers (fixed addresses), the whole step -- including the nested
+// conditional IF nodes around every post-exit segment -- is replayed with one cudaGraphLaunch, outputs are copied out.
+static int step_graph(deer_ctx* c, int n, const int32_t* slots, const float* rgb, const float* gripper, const int64_t* ids,
+                      const uint8_t* mask, int S, const int32_t* timesteps, int static_exit, uint32_t flags, float* pose_out,
+                      float* gripper_out, float* action_out, int32_t* exit_out, float* delta_out, cudaStream_t st) {
+  const size_t img = (size_t)3 * c->cfg.image_size * c->cfg.image_size * 4;
+  auto stage = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+    return (dst == src) ? cudaSuccess : cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st);
+  };
+  CK(stage(c->s_rgb, rgb, n * img));
+  CK(stage(c->s_grip, gripper, n * img));
+  CK(stage(c->s_ids, ids, (size_t)n * S * 8));
+  CK(stage(c->s_mask, mask, (size_t)n * S));
+  CK(stage(c->s_slots, slots, (size_t)n * 4));
+  if (timesteps) CK(stage(c->s_ts, timesteps, (size_t)n * 4));
+  auto key = std::make_tuple(n, S, static_exit, flags, timesteps ? 1 : 0);
+  deer_ctx::GraphEntry& ge = c->graphs[key];
+  int r = DEER_OK;
+  if (ge.exec == nullptr && ge.seen == 0) {
+    // first use of this shape: run eagerly once (sets function attributes, builds the TMA descriptors)
+    ge.seen = 1;
+    r = step_dispatch(c, n, c->s_slots, c->s_rgb, c->s_grip, c->s_ids, c->s_mask, S, timesteps ? c->s_ts : nullptr, static_exit, flags,
+                      c->o_pose, c->o_grip, c->o_action, c->o_exit, c->o_delta, st);
+    if (r != DEER_OK) return r;
+  } else {
+    if (ge.exec == nullptr) {
+      CK(cudaStreamSynchronize(st));
+      CK(cudaGraphCreate(&ge.graph, 0));
+      if (!c->cap_streams[0]) CK(cudaStreamCreateWithFlags(&c->cap_streams[0], cudaStreamNonBlocking));
+      CK(cudaStreamBeginCaptureToGraph(c->cap_streams[0], ge.graph, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+      c->cap_level = 0;
+      r = step_dispatch(c, n, c->s_slots, c->s_rgb, c->s_grip, c->s_ids, c->s_mask, S, timesteps ? c->s_ts : nullptr, static_exit, flags,
+                        c->o_pose, c->o_grip, c->o_action, c->o_exit, c->o_delta, c->cap_streams[0]);
+      // close the nested captures from the innermost conditional body outwards
+      cudaError_t ce = cudaSuccess;
+      for (int lvl = c->cap_level; lvl >= 0; --lvl) {
+        cudaGraph_t out = nullptr;
+        cudaError_t e2 = cudaStreamEndCapture(c->cap_streams[lvl], &out);
+        if (e2 != cudaSuccess && ce == cudaSuccess) ce = e2;
+      }
+      c->cap_level = -1;
+      if (r != DEER_OK) return r;
+      if (ce != cudaSuccess) return set_err(&c->err, DEER_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+      CK(cudaGraphInstantiate(&ge.exec, ge.graph, 0));
+      ge.launches = c->stats.step; ge.gemms = c->stats.gemm_step; ge.flops = c->stats.gemm_flops_step; ge.probes = c->n_probes_last;
+      c->graphs_built++;
+    }
+    CK(cudaGraphLaunch(ge.exec, st));
+    c->graph_launches++;
+    c->stats.step = ge.launches; c->stats.gemm_step = ge.gemms; c->stats.gemm_flops_step = ge.flops; c->stats.total += ge.launches;
+    c->n_probes_last = ge.probes; c->n_last = n; c->tap_n = n; c->tap_S = S;
+  }
+  if (pose_out && pose_out != c->o_pose) CK(cudaMemcpyAsync(pose_out, c->o_pose, (size_t)n * 6 * 4, cudaMemcpyDeviceToDevice, st));
+  if (gripper_out && gripper_out != c->o_grip) CK(cudaMemcpyAsync(gripper_out, c->o_grip, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  if (action_out && action_out != c->o_action) CK(cudaMemcpyAsync(action_out, c->o_action, (size_t)n * 7 * 4, cudaMemcpyDeviceToDevice, st));
+  if (exit_out && exit_out != c->o_exit) CK(cudaMemcpyAsync(exit_out, c->o_exit, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  if (delta_out && delta_out != c->o_delta && c->n_thr > 0) CK(cudaMemcpyAsync(delta_out, c->o_delta, (size_t)n * c->n_thr * 4, cudaMemcpyDeviceToDevice, st));
+  return DEER_OK;
+}
+
 extern "C" int deer_step(deer_ctx* c, int n, const int32_t* slots, const float* rgb, const float* gripper, const int64_t* ids,
                          const uint8_t* mask, int S, const int32_t* timesteps, int static_exit, uint32_t flags, float* pose_out,
                          float* gripper_out, float* action_out, int32_t* exit_out, float* delta_out, void* stream) {
@@ -1102,10 +1204,10 @@ extern "C" int deer_step(deer_ctx* c, int n, const int32_t* slots, const float* 
   c->stats.step = 0; c->stats.gemm_step = 0; c->stats.gemm_flops_step = 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int r;
-  if (c->dtype == 1)
-    r = step_impl<float>(c, n, slots, rgb, gripper, ids, mask, S, timesteps, static_exit, flags, pose_out, gripper_out, action_out, exit_out, delta_out, st);
+  if (c->cfg.use_graph && !c->cfg.host_control && !c->gemm.profile)
+    r = step_graph(c, n, slots, rgb, gripper, ids, mask, S, timesteps, static_exit, flags, pose_out, gripper_out, action_out, exit_out, delta_out, st);
   else
-    r = step_impl<bf16>(c, n, slots, rgb, gripper, ids, mask, S, timesteps, static_exit, flags, pose_out, gripper_out, action_out, exit_out, delta_out, st);
+    r = step_dispatch(c, n, slots, rgb, gripper, ids, mask, S, timesteps, static_exit, flags, pose_out, gripper_out, action_out, exit_out, delta_out, st);
   if (r == DEER_OK) c->steps++;
   return r;
 }

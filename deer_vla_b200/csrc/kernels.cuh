@@ -381,6 +381,9 @@ struct GateParams {
   // compaction
   uint8_t* exit_flag;        // [r] this episode leaves now
   int* src_of_new;           // [r'] source rank of survivor r'
+  // CUDA-graph control flow: when has_cond, the conditional IF node that wraps every later layer runs iff survivors remain
+  cudaGraphConditionalHandle cond;
+  int has_cond;
 };
 
 __global__ void __launch_bounds__(1024)
@@ -461,7 +464,11 @@ exit_gate_kernel(GateParams g, EpisodeMeta m, const int* __restrict__ n_cur, int
   __syncthreads();
   const int pos = wsum[warp] + incl - survive;
   if (survive) g.src_of_new[pos] = r;
-  if (threadIdx.x == 0) { *n_next = total; *hist = total; }
+  if (threadIdx.x == 0) {
+    *n_next = total;
+    *hist = total;
+    if (g.has_cond) cudaGraphSetConditional(g.cond, total > 0 ? 1u : 0u);
+  }
 }
 
 // commit the candidate LSTM state of the episodes that exit now (update_hidden_state=True, action_head.py:554-556)

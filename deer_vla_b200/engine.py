@@ -27,7 +27,7 @@ class DeerEngine:
 
     def __init__(self, cfg: DeerConfig, max_batch: int = 1, max_slots: Optional[int] = None, max_seq: int = 32,
                  device: int = 0, precision: str = "bf16", gemm_impl: str = "tcgen05", debug_taps: bool = False,
-                 host_control: bool = False):
+                 host_control: bool = False, use_graph: bool = False):
         self.lib = _lib.load()
         self.cfg = cfg
         self.device = torch.device("cuda", device)
@@ -54,6 +54,7 @@ class DeerEngine:
         cc.gemm_impl = {"tcgen05": _lib.GEMM_TCGEN05, "simt": _lib.GEMM_SIMT}[gemm_impl]
         cc.debug_taps = int(debug_taps)
         cc.host_control = int(host_control)
+        cc.use_graph = int(use_graph)
         self.precision = precision
         self._h = C.c_void_p()
         rc = self.lib.deer_create(C.byref(cc), device, C.byref(self._h))

@@ -81,6 +81,10 @@ typedef struct deer_config {
   int32_t host_control;      /* 1: read the active count back after every probe (the reference's
                                 per-probe D2H sync, value_net.py:293) and stop launching when 0;
                                 0: fully device-side control flow, no host sync inside a step */
+  int32_t use_graph;         /* 1 (needs host_control=0): each (n, S, mode) step is captured ONCE into a CUDA graph whose
+                                post-exit segments are nested conditional IF nodes; exit_gate_kernel sets the condition
+                                (cudaGraphSetConditional) from the device-side active count, so the layers past the
+                                last active episode's exit are never launched and no host round trip is needed */
 } deer_config;
 
 typedef struct deer_stats {

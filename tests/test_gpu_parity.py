@@ -131,6 +131,38 @@ def test_tiny_golden_batched_equals_single(tiny, gold_tiny):
         eng.close()
 
 
+def test_tiny_golden_cuda_graph_conditional_exit(tiny, gold_tiny):
+    """use_graph=1: the step is captured once into a CUDA graph whose post-exit segments are nested conditional IF nodes
+    driven by exit_gate_kernel (cudaGraphSetConditional).  Step 0 runs eagerly, step 1 captures, later steps replay; every
+    step must reproduce the reference's golden exits / poses, for a batch whose episodes leave at different exits."""
+    ocfg, W = tiny
+    g = gold_tiny
+    S, T = int(g["S"]), int(g["T"])
+    eps = g["episodes"].tolist()
+    for prec, tol in (("fp32", 2e-4),):
+        eng = _engine(ocfg, W, max_batch=len(eps), max_seq=S, precision=prec, use_graph=True)
+        eng.set_thresholds(g["thresholds"].tolist())
+        eng.reset()
+        for t in range(T):
+            rgb, grip, ids = _inputs(ocfg, eps, t, S)
+            out = eng.step(rgb.cuda(), grip.cuda(), ids.cuda())
+            ex = out["exit_layer"].cpu().numpy()
+            pose = out["pose"].cpu().numpy()
+            for i, e in enumerate(eps):
+                assert int(ex[i]) == int(g[f"ep{e}_exit_layer"][t]), (t, e, ex)
+                assert np.abs(pose[i] - g[f"ep{e}_pose"][t]).max() <= tol
+        eng.close()
+    # single episode: when it exits at layer 1 every later layer sits inside a conditional node that must not run
+    eng = _engine(ocfg, W, max_batch=1, max_seq=S, precision="fp32", use_graph=True)
+    eng.set_thresholds(g["thresholds"].tolist())
+    for e in eps[:2]:
+        res = _run_golden_episode(eng, ocfg, e, T, S)
+        for t in range(T):
+            assert int(res[t]["exit_layer"][0]) == int(g[f"ep{e}_exit_layer"][t]), (e, t)
+            assert np.abs(res[t]["pose"][0] - g[f"ep{e}_pose"][t]).max() <= 2e-4
+    eng.close()
+
+
 def test_tiny_steps_per_stage_and_max_layer(tiny, gold_tiny):
     """value_net.py:285-286 (steps_per_stage=2 reuses the previous exit id on odd steps) and the
     max_layer=4 truncation (exit list [1,3,4], forced exit at 3; eval_calvin.py:529, value_net.py:173)."""
@@ -204,6 +236,33 @@ def test_errors_mirror_reference_asserts(tiny):
         eng.set_thresholds([0.1])
     with pytest.raises(DeerError):           # 0 <= exit_id < n_layers (flamingo_mpt.py:449)
         eng.step(rgb.cuda(), grip.cuda(), ids.cuda(), exit_id=17)
+    eng.close()
+
+
+def test_tiny_9b_geometry_vs_oracle():
+    """OpenFlamingo-9B structure (MPT-7B block: no q/k LayerNorm, norm_1/norm_2/ffn.* names; x-attn only every 4th layer;
+    exits [1,3,...,12] with max_layer=12 forcing the exit at 11) at reduced dims, fp32 path vs the oracle."""
+    ocfg = O.config_tiny(d_model=256, n_heads=2, qk_ln=False, cross_attn_every=4, llm_name="mpt_9b",
+                         ckpt_early_exit_layer=15, max_layer=12)
+    assert ocfg.exit_list == [1, 3, 5, 7, 9, 11, 12] and ocfg.ctrl_max_layer == 11 and ocfg.n_thresholds == 6
+    W = O.synth_weights(ocfg, 2)
+    S = 10
+    eng = _engine(ocfg, W, max_batch=2, max_seq=S, precision="fp32", debug_taps=True)
+    assert eng.exit_list == ocfg.exit_list
+    thr = [-1e8, 0.2, 0.2, 0.2, 0.2, 1e8]            # p_0 = 0 for mpt_9b: the first exit never fires (value_net.py:235-236)
+    eng.set_thresholds(thr)
+    eng.reset()
+    for t in range(2):
+        rgb, grip, ids = _inputs(ocfg, [0, 1], t, S)
+        out = eng.step(rgb.cuda(), grip.cuda(), ids.cuda())
+        for e in range(2):
+            if t == 0:
+                orc = O.DeerOracle(ocfg, W, thr)
+                o = orc.step(rgb[e], grip[e], ids[e], taps=True)
+                for l in range(o.exit_layer + 1):
+                    assert np.abs(eng.get_tap("hidden", l)[e] - o.taps[f"hidden_{l}"].numpy()).max() <= 3e-4, l
+                assert int(out["exit_layer"][e]) == o.exit_layer and o.exit_layer >= 3
+                assert np.abs(out["pose"][e].cpu().numpy() - o.pose.numpy()).max() <= 2e-4
     eng.close()
 
 
