@@ -261,8 +261,15 @@ def engine_arm(a):
     stages = {k: {"ms_per_step": prof_acc["gemm_ms"][k] / prof_acc["n"],
                   "tflops": (prof_acc["gemm_flops"][k] / (prof_acc["gemm_ms"][k] * 1e-3) / 1e12) if prof_acc["gemm_ms"][k] > 0 else 0.0,
                   "launches_per_step": prof_acc["gemm_launches"][k] // prof_acc["n"]} for k in prof_acc["gemm_ms"]}
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<BN> (tcgen05.mma + TMA, all GEMM launches of a step)",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+    traffic, tensor_pct = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(tp) and a.workload == "deer_b" and B == 224:      # ncu capture of exactly this workload (committed summary)
+        tj = json.load(open(tp))
+        traffic, tensor_pct = tj["traffic_bytes_per_launch"], tj["tensor_pipe_active_pct_time_weighted"]
+    roofline = {"bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel<BN> (tcgen05.mma + TMA; every GEMM launch of a step)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                "traffic_source": "profiles/r01_gemm_traffic.json (ncu dram__bytes_read+write per launch)" if traffic else None,
+                "tensor_pipe_active_pct_ncu": tensor_pct,
                 "peak_source": peak_src, "algorithmic_flops_per_launch": g_fl / max(1, g_n),
                 "avg_launch_ms": g_ms / max(1, g_n), "gemm_share_of_step": g_ms / prof_acc["step_ms"] if prof_acc["step_ms"] else None,
                 "stages": stages, "active_after_each_exit": prof_acc.get("active_after")}
