@@ -112,15 +112,78 @@ attn_small_kernel(AttnParams p) {
   const T* V = reinterpret_cast<const T*>(p.V) + static_cast<size_t>(b) * Sk * p.ldv + h * hd;
   T* O = reinterpret_cast<T*>(p.O) + static_cast<size_t>(b) * Sq * p.ldo + h * hd;
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < Sq * hd; idx += 256) { const int i = idx / hd, d = idx % hd; sq[i * hp + d] = to_f32<T>(Q[static_cast<size_t>(i) * p.ldq + d]); }
-  for (int idx = tid; idx < Sk * hd; idx += 256) {
-    const int j = idx / hd, d = idx % hd;
-    sk[j * hp + d] = to_f32<T>(K[static_cast<size_t>(j) * p.ldk + d]);
-    sv[j * hp + d] = to_f32<T>(V[static_cast<size_t>(j) * p.ldv + d]);
+  // stage Q, K, V as fp32 (16-byte global loads: 8 bf16 or 4 floats per thread per request)
+  constexpr int VE = 16 / sizeof(T);
+  const bool vec = (hd % VE == 0) && (p.ldq % VE == 0) && (p.ldk % VE == 0) && (p.ldv % VE == 0);
+  if (vec) {
+    const int hv = hd / VE;
+    for (int idx = tid; idx < Sq * hv; idx += 256) {
+      const int i = idx / hv, c = idx % hv;
+      T tmp[VE];
+      *reinterpret_cast<uint4*>(tmp) = *reinterpret_cast<const uint4*>(Q + static_cast<size_t>(i) * p.ldq + c * VE);
+#pragma unroll
+      for (int e = 0; e < VE; ++e) sq[i * hp + c * VE + e] = to_f32<T>(tmp[e]);
+    }
+    for (int idx = tid; idx < Sk * hv; idx += 256) {
+      const int j = idx / hv, c = idx % hv;
+      T tk[VE], tv[VE];
+      *reinterpret_cast<uint4*>(tk) = *reinterpret_cast<const uint4*>(K + static_cast<size_t>(j) * p.ldk + c * VE);
+      *reinterpret_cast<uint4*>(tv) = *reinterpret_cast<const uint4*>(V + static_cast<size_t>(j) * p.ldv + c * VE);
+#pragma unroll
+      for (int e = 0; e < VE; ++e) { sk[j * hp + c * VE + e] = to_f32<T>(tk[e]); sv[j * hp + c * VE + e] = to_f32<T>(tv[e]); }
+    }
+  } else {
+    for (int idx = tid; idx < Sq * hd; idx += 256) { const int i = idx / hd, d = idx % hd; sq[i * hp + d] = to_f32<T>(Q[static_cast<size_t>(i) * p.ldq + d]); }
+    for (int idx = tid; idx < Sk * hd; idx += 256) {
+      const int j = idx / hd, d = idx % hd;
+      sk[j * hp + d] = to_f32<T>(K[static_cast<size_t>(j) * p.ldk + d]);
+      sv[j * hp + d] = to_f32<T>(V[static_cast<size_t>(j) * p.ldv + d]);
+    }
   }
   __syncthreads();
   const int kvl = p.kv_len ? p.kv_len[b] : Sk;
   const float slope = p.alibi_slopes ? p.alibi_slopes[h] : 0.0f;
+  const bool tiled = (Sq <= 32) && (Sk <= 128) && (hd <= 128);
+  if (tiled) {
+    // register-tiled scores: thread (g = tid/32, t = tid%32) owns queries 4g..4g+3 x keys t, t+32, t+64, t+96
+    // (q values are warp broadcasts, key rows t + 32r hit 32 distinct banks: 8 LDS per 16 FMA instead of 2 per 1)
+    const int g = tid >> 5, t = tid & 31;
+    const int kpt = (Sk + 31) >> 5;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[a][r] = 0.0f;
+    for (int d = 0; d < hd; ++d) {
+      float qv[4], kv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) qv[a] = (4 * g + a < Sq) ? sq[(4 * g + a) * hp + d] : 0.0f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) kv[r] = (r < kpt && t + 32 * r < Sk) ? sk[(t + 32 * r) * hp + d] : 0.0f;
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[a][r] = fmaf(qv[a], kv[r], acc[a][r]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = 4 * g + a;
+      if (i < Sq) {
+        const int mode = p.qmode ? p.qmode[b * Sq + i] : 1;
+        const int jmax = p.causal ? (i + (Sk - Sq)) : (Sk - 1);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int j = t + 32 * r;
+          if (j < Sk) {
+            float sv_ = acc[a][r] * p.scale + slope * static_cast<float>(j - (Sk - 1));
+            if (mode == 2) sv_ = 0.0f;
+            else if (j > jmax || j >= kvl) sv_ = -INFINITY;
+            ss[i * skp + j] = sv_;
+          }
+        }
+      }
+    }
+  } else {
   for (int idx = tid; idx < Sq * Sk; idx += 256) {
     const int i = idx / Sk, j = idx % Sk;          // consecutive threads -> consecutive keys (distinct smem rows)
     const int mode = p.qmode ? p.qmode[b * Sq + i] : 1;
@@ -134,6 +197,7 @@ attn_small_kernel(AttnParams p) {
     if (mode == 2) s = 0.0f;
     else if (j > jmax || j >= kvl) s = -INFINITY;
     ss[i * skp + j] = s;
+  }
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
@@ -154,12 +218,45 @@ attn_small_kernel(AttnParams p) {
     for (int j = lane; j < Sk; j += 32) ss[i * skp + j] *= inv;
   }
   __syncthreads();
+  if (tiled) {
+    // register-tiled PV: thread owns queries 4g..4g+3 x output dims t, t+32, t+64, t+96
+    const int g = tid >> 5, t = tid & 31;
+    const int dpt = (hd + 31) >> 5;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[a][r] = 0.0f;
+    for (int j = 0; j < Sk; ++j) {
+      float pv[4], vv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) pv[a] = (4 * g + a < Sq) ? ss[(4 * g + a) * skp + j] : 0.0f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) vv[r] = (r < dpt && t + 32 * r < hd) ? sv[j * hp + t + 32 * r] : 0.0f;
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[a][r] = fmaf(pv[a], vv[r], acc[a][r]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = 4 * g + a;
+      if (i < Sq) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int d = t + 32 * r;
+          if (d < hd) O[static_cast<size_t>(i) * p.ldo + d] = from_f32<T>(acc[a][r]);
+        }
+      }
+    }
+  } else {
   for (int idx = tid; idx < Sq * hd; idx += 256) {
     const int i = idx / hd, d = idx % hd;              // consecutive threads -> consecutive d (conflict-free V reads)
     float acc = 0.0f;
     const float* pr = ss + i * skp;
     for (int j = 0; j < Sk; ++j) acc = fmaf(pr[j], sv[j * hp + d], acc);
     O[static_cast<size_t>(i) * p.ldo + d] = from_f32<T>(acc);
+  }
   }
 }
 static inline size_t attn_small_smem(int Sq, int Sk, int hd) { return (static_cast<size_t>(Sq + 2 * Sk) * (hd + 1) + static_cast<size_t>(Sq) * (Sk + 1)) * sizeof(float); }
