@@ -61,6 +61,9 @@ SYMBOLS = {
     "deer_reset": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_int]),
     "deer_step": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_uint32, _P, _P, _P, _P, _P, _P]),
     "deer_step_host": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_uint32, _P, _P, _P, _P, _P]),
+    "deer_preprocess_u8": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "deer_step_host_u8": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_uint32,
+                                    _P, _P, _P, _P, _P]),
     "deer_get_state": (C.c_int, [_P, C.c_int, _P, _P]),
     "deer_get_tap": (C.c_int, [_P, C.c_char_p, C.c_int, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "deer_get_stats": (C.c_int, [_P, C.POINTER(DeerStats)]),

@@ -1,0 +1,100 @@
+"""DeeR checkpoint handling (robot_flamingo/eval/eval_calvin.py:356-489, robot_flamingo/train/train_utils.py:27-60,631-638).
+
+A DeeR ``.pth`` is a dict: ``model_state_dict`` (trainable tensors only, keys prefixed ``module.``), head hyper-parameters
+(``head_type, early_exit_layer, multi_exit, exit_interval, mlp_layernorm, lstm_layernorm, mlp_num_hidden_layers,
+lstm_num_layers, pooling`` ...), optionally the cached delta table ``values`` (eval_calvin.py:601-611), optimizer state.
+More configuration is smuggled through the FILE NAME and re-parsed at evaluation time.  This module restates that
+bookkeeping for the engine and refuses configurations the engine does not implement instead of silently diverging.
+"""
+from __future__ import annotations
+
+import os
+import re
+from typing import Any, Dict, Mapping, Optional
+
+from .config import DeerConfig, config_3b, config_9b
+
+LLM_NAMES = ["mpt_3b", "mpt_4b", "mpt_9b", "mpt_dolly_3b", "mpt_base_4b"]          # eval_calvin.py:417
+_N_LAYERS = {"mpt_3b": 24, "mpt_dolly_3b": 24, "mpt_9b": 32}                        # eval_calvin.py:481-487
+
+
+def parse_checkpoint_name(path: str, default_llm: str = "mpt_dolly_3b") -> Dict[str, Any]:
+    """Flags derived from the checkpoint file name exactly as eval_calvin.py:356-421 does (substring tests included)."""
+    name = path
+    out: Dict[str, Any] = {}
+    out["use_state"] = "state" in name
+    out["real_data"] = "real" in name
+    m = re.search(r"aug_(\d+)_(\d+)", name)
+    out["rgb_pad"], out["gripper_pad"] = (int(m.group(1)), int(m.group(2))) if m else (-1, -1)
+    out["sep_resampler"] = "sep" in name
+    out["sep_lm_head"] = "lm_head" in name
+    out["residual"] = "res_" in name
+    out["tcp_rel"] = "tcp" in name
+    parts = name.split("_")
+    out["multi_step_action"] = int(parts[parts.index("step") - 1]) if "step" in parts else 1
+    out["text_aug"] = "text_aug" in name
+    out["traj_cons"] = "traj_cons" in name
+    if "difws" in name:
+        ix = parts.index("difws")
+        out["dif_ws"], out["min_window_size"], out["max_window_size"] = True, int(parts[ix + 1]), int(parts[ix + 2])
+        out["window_size"] = out["max_window_size"]
+    else:
+        out["dif_ws"] = False
+    if "latent" in name:
+        out["global_latent"] = int(parts[parts.index("latent") + 1])
+    out["no_image_patch"] = "no_image_patch" in name
+    if "gpt" in name:
+        out["decoder_type"], out["hidden_size"] = "gpt", int(parts[parts.index("gpt") + 1])
+    out["llm_name"] = default_llm
+    for n in LLM_NAMES:                           # first match in this order wins, like the reference's loop
+        if n in name:
+            out["llm_name"] = n
+            break
+    return out
+
+
+def readout_args(ckpt: Mapping[str, Any], llm_name: str, max_layer: Optional[int] = None) -> Dict[str, Any]:
+    """Head hyper-parameters with the reference's defaults for old checkpoints (eval_calvin.py:455-489)."""
+    defaults = dict(head_type="deterministic", early_exit_layer=-1, multi_exit=False, exit_interval=1, exit_dropout=0.0,
+                    lstm_dropout=0.0, dropout_mode="wo_last", mlp_layernorm=False, lstm_layernorm=False,
+                    mlp_num_hidden_layers=3, lstm_num_layers=4, pooling="max")
+    a = {k: ckpt.get(k, v) for k, v in defaults.items()}
+    if "layernorm" in ckpt:                       # compatibility with old code
+        a["mlp_layernorm"] = ckpt["layernorm"]
+    if a["early_exit_layer"] < 0:
+        if llm_name not in _N_LAYERS:
+            raise NotImplementedError(llm_name)
+        a["early_exit_layer"] += _N_LAYERS[llm_name]
+    a["max_layer"] = a["early_exit_layer"] + 1 if max_layer in (None, -1) else max_layer
+    return a
+
+
+def config_from_checkpoint(ckpt: Mapping[str, Any], path: str = "", max_layer: Optional[int] = None,
+                           steps_per_stage: int = 1, threshold_type: str = "L2") -> DeerConfig:
+    """DeerConfig for a DeeR checkpoint; raises for configurations outside the engine's scope."""
+    flags = parse_checkpoint_name(os.path.basename(path)) if path else {"llm_name": "mpt_dolly_3b"}
+    a = readout_args(ckpt, flags["llm_name"], max_layer)
+    unsupported = []
+    if a["head_type"] != "deterministic":
+        unsupported.append(f"head_type={a['head_type']}")
+    if not (a["mlp_layernorm"] and a["lstm_layernorm"] and a["mlp_num_hidden_layers"] == 2 and a["dropout_mode"] == "layerwise"):
+        unsupported.append("head variant other than the trained DeeR config (layerwise dropout, LayerNorm MLP/LSTM, 2 hidden layers; "
+                           "train_calvin_post_strategy.py:336-344)")
+    if a["pooling"] != "max":
+        unsupported.append(f"pooling={a['pooling']}")
+    for k in ("use_state", "sep_resampler", "residual", "tcp_rel", "no_image_patch"):
+        if flags.get(k):
+            unsupported.append(k)
+    if flags.get("multi_step_action", 1) != 1 or flags.get("decoder_type", "lstm") != "lstm":
+        unsupported.append("multi_step_action / gpt decoder")
+    if unsupported:
+        raise NotImplementedError("checkpoint needs features outside the engine's scope: " + "; ".join(unsupported))
+    build = config_9b if "mpt_9b" in flags["llm_name"] else config_3b
+    return build(a["max_layer"], ckpt_early_exit_layer=a["early_exit_layer"], exit_interval=a["exit_interval"],
+                 lstm_layers=a["lstm_num_layers"], steps_per_stage=steps_per_stage, threshold_type=threshold_type,
+                 llm_name=flags["llm_name"])
+
+
+def state_dict_of(ckpt: Mapping[str, Any]) -> Mapping[str, Any]:
+    """``model_state_dict`` if present (DeeR .pth), else the mapping itself (OpenFlamingo .pt / plain state dict)."""
+    return ckpt.get("model_state_dict", ckpt)

@@ -313,6 +313,10 @@ struct deer_ctx {
   cudaStream_t cap_streams[20] = {nullptr};
   int cap_level = -1;                 // >= 0 while a step is being captured
   int64_t graph_launches = 0, graphs_built = 0;
+  // on-device image transform: Pillow coefficient tables per (in_size -> out_size), uint8 staging
+  struct AxisTab { int* bounds = nullptr; int* kk = nullptr; int ksize = 0; int need = 0; };
+  std::map<std::pair<int, int>, AxisTab> axis_tabs;
+  uint8_t* u8_stage[2] = {nullptr, nullptr}; size_t u8_cap[2] = {0, 0};
   GemmCtx gemm;
   LaunchStats stats;
   int64_t steps = 0;
@@ -578,6 +582,7 @@ extern "C" void deer_destroy(deer_ctx* c) {
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   for (auto& kv : c->graphs) { if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec); if (kv.second.graph) cudaGraphDestroy(kv.second.graph); }
   for (auto s2 : c->cap_streams) if (s2) cudaStreamDestroy(s2);
+  for (int k = 0; k < 2; ++k) if (c->u8_stage[k]) cudaFree(c->u8_stage[k]);
   delete c;
 }
 
@@ -1368,5 +1373,112 @@ extern "C" int deer_attn_debug(int enable, long long* host_out, int n) {
   if (enable && !g_attn_dbg) { cudaMalloc(reinterpret_cast<void**>(&g_attn_dbg), 512 * 8 * sizeof(long long)); cudaMemset(g_attn_dbg, 0, 512 * 8 * sizeof(long long)); }
   if (host_out && g_attn_dbg) { cudaDeviceSynchronize(); cudaMemcpy(host_out, g_attn_dbg, std::min(n, 512 * 8) * sizeof(long long), cudaMemcpyDeviceToHost); }
   if (!enable && g_attn_dbg) { cudaFree(g_attn_dbg); g_attn_dbg = nullptr; }
+  return DEER_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// on-device image transform
+// ---------------------------------------------------------------------------------------------
+static double pil_bicubic(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+// Pillow src/libImaging/Resample.c: precompute_coeffs + normalize_coeffs_8bpc (box = the whole axis)
+static int get_axis(deer_ctx* c, int in_size, int out_size, ResizeAxis* out) {
+  auto key = std::make_pair(in_size, out_size);
+  auto it = c->axis_tabs.find(key);
+  if (it == c->axis_tabs.end()) {
+    deer_ctx::AxisTab t;
+    t.need = (in_size != out_size);
+    if (t.need) {
+      const double scale = (double)in_size / out_size;
+      const double filterscale = scale < 1.0 ? 1.0 : scale;
+      const double support = 2.0 * filterscale;
+      t.ksize = (int)std::ceil(support) * 2 + 1;
+      std::vector<int> bounds(2 * out_size), kk((size_t)out_size * t.ksize, 0);
+      std::vector<double> w(t.ksize);
+      const double ss = 1.0 / filterscale;
+      for (int xx = 0; xx < out_size; ++xx) {
+        const double center = 0.0 + (xx + 0.5) * scale;
+        int xmin = (int)(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = (int)(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        xmax -= xmin;
+        double ww = 0.0;
+        for (int x = 0; x < xmax; ++x) { w[x] = pil_bicubic((x + xmin - center + 0.5) * ss); ww += w[x]; }
+        for (int x = 0; x < xmax; ++x) {
+          const double v = (ww != 0.0) ? w[x] / ww : w[x];
+          kk[(size_t)xx * t.ksize + x] = v < 0 ? (int)(-0.5 + v * (1 << 22)) : (int)(0.5 + v * (1 << 22));
+        }
+        bounds[2 * xx] = xmin; bounds[2 * xx + 1] = xmax;
+      }
+      RET(dalloc(c, reinterpret_cast<void**>(&t.bounds), bounds.size() * 4, false));
+      RET(dalloc(c, reinterpret_cast<void**>(&t.kk), kk.size() * 4, false));
+      CK(cudaMemcpy(t.bounds, bounds.data(), bounds.size() * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(t.kk, kk.data(), kk.size() * 4, cudaMemcpyHostToDevice));
+    }
+    it = c->axis_tabs.emplace(key, t).first;
+  }
+  out->bounds = it->second.bounds; out->kk = it->second.kk; out->ksize = it->second.ksize; out->need = it->second.need;
+  return DEER_OK;
+}
+
+extern "C" int deer_preprocess_u8(deer_ctx* c, const uint8_t* frames, int n, int H, int W, float* out, void* stream) {
+  if (!c || !frames || !out) return set_err(c ? &c->err : nullptr, DEER_E_INVALID, "null argument");
+  if (n < 1 || H < 1 || W < 1 || H > 8192 || W > 8192) return set_err(&c->err, DEER_E_INVALID, "bad image dims");
+  cudaSetDevice(c->device);
+  const int size = c->cfg.image_size;
+  // torchvision Resize(size:int): smaller edge -> size, other edge -> int(size * long / short); then CenterCrop(size)
+  int nh, nw;
+  if (H <= W) { nh = size; nw = (int)((double)size * W / H); } else { nw = size; nh = (int)((double)size * H / W); }
+  const int top = (int)std::nearbyint((nh - size) / 2.0), left = (int)std::nearbyint((nw - size) / 2.0);
+  ResizeAxis ax, ay;
+  RET(get_axis(c, W, nw, &ax));
+  RET(get_axis(c, H, nh, &ay));
+  dim3 grid((size * size + 255) / 256, n);
+  preprocess_u8_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(frames, n, H, W, ax, ay, top, left, size, out);
+  KLAUNCH_CHECK("preprocess_u8");
+  return DEER_OK;
+}
+
+extern "C" int deer_step_host_u8(deer_ctx* c, int n, const int32_t* slots, const uint8_t* rgb, int Hs, int Ws, const uint8_t* gripper,
+                                 int Hg, int Wg, const int64_t* ids, const uint8_t* mask, int S, const int32_t* timesteps,
+                                 int static_exit, uint32_t flags, float* pose_out, float* gripper_out, float* action_out,
+                                 int32_t* exit_out, float* delta_out) {
+  if (!c) return set_err(nullptr, DEER_E_INVALID, "null ctx");
+  if (!slots || !rgb || !gripper || !ids || !mask) return set_err(&c->err, DEER_E_INVALID, "null input pointer");
+  RET(validate_step(c, n, S, static_exit, flags));
+  for (int i = 0; i < n; ++i)
+    if (slots[i] < 0 || slots[i] >= c->cfg.max_slots) return set_err(&c->err, DEER_E_INVALID, "slot %d out of range", slots[i]);
+  cudaSetDevice(c->device);
+  cudaStream_t st = c->own_stream;
+  const size_t bytes[2] = {(size_t)n * Hs * Ws * 3, (size_t)n * Hg * Wg * 3};
+  for (int k = 0; k < 2; ++k)
+    if (c->u8_cap[k] < bytes[k]) {
+      if (c->u8_stage[k]) cudaFree(c->u8_stage[k]);
+      const size_t cap = std::max(bytes[k], (size_t)c->cfg.max_batch * (k == 0 ? Hs * Ws : Hg * Wg) * 3);
+      CK(cudaMalloc(reinterpret_cast<void**>(&c->u8_stage[k]), cap));
+      c->u8_cap[k] = cap;
+    }
+  CK(cudaMemcpyAsync(c->u8_stage[0], rgb, bytes[0], cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(c->u8_stage[1], gripper, bytes[1], cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(c->s_ids, ids, (size_t)n * S * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(c->s_mask, mask, (size_t)n * S, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(c->s_slots, slots, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  if (timesteps) CK(cudaMemcpyAsync(c->s_ts, timesteps, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  RET(deer_preprocess_u8(c, c->u8_stage[0], n, Hs, Ws, c->s_rgb, st));
+  RET(deer_preprocess_u8(c, c->u8_stage[1], n, Hg, Wg, c->s_grip, st));
+  RET(deer_step(c, n, c->s_slots, c->s_rgb, c->s_grip, c->s_ids, c->s_mask, S, timesteps ? c->s_ts : nullptr, static_exit, flags,
+                c->o_pose, c->o_grip, c->o_action, c->o_exit, c->o_delta, st));
+  if (pose_out) CK(cudaMemcpyAsync(pose_out, c->o_pose, (size_t)n * 6 * 4, cudaMemcpyDeviceToHost, st));
+  if (gripper_out) CK(cudaMemcpyAsync(gripper_out, c->o_grip, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (action_out) CK(cudaMemcpyAsync(action_out, c->o_action, (size_t)n * 7 * 4, cudaMemcpyDeviceToHost, st));
+  if (exit_out) CK(cudaMemcpyAsync(exit_out, c->o_exit, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (delta_out && c->n_thr > 0) CK(cudaMemcpyAsync(delta_out, c->o_delta, (size_t)n * c->n_thr * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return DEER_OK;
 }

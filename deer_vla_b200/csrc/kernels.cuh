@@ -543,3 +543,58 @@ __global__ void convert_kernel(const float* __restrict__ src, T* __restrict__ ds
     dst[r * dst_ld + dst_col_off + c] = from_f32<T>(src[r * src_ld + c]);
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// On-device image transform (replaces the host PIL path in front of the hot path: data.py:898-902 -> open_clip
+// image_transform): Resize(size, BICUBIC) -> CenterCrop(size) -> /255 -> Normalize(CLIP mean, std), uint8 HWC in,
+// fp32 CHW out.  The resize reproduces Pillow's 8-bit resampler BIT-EXACTLY: horizontal pass then vertical pass, 22-bit
+// fixed-point coefficients (tables built on the host with Pillow's own double arithmetic), int32 accumulation starting at
+// 1<<21, arithmetic shift, clamp to [0,255], uint8 round-trip between the passes.  One thread per output pixel.
+// ---------------------------------------------------------------------------------------------
+struct ResizeAxis { const int* bounds; const int* kk; int ksize; int need; };   // bounds[out][2] = (min, count); kk[out][ksize]
+
+__device__ __forceinline__ int clip8_fixed(int v) {
+  v >>= 22;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+__global__ void __launch_bounds__(256)
+preprocess_u8_kernel(const uint8_t* __restrict__ img, int n, int H, int W, ResizeAxis ax, ResizeAxis ay, int top, int left, int size,
+                     float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= size * size || b >= n) return;
+  const int oy = idx / size, ox = idx % size;
+  const int ry = oy + top, rx = ox + left;                      // coordinates in the resized (pre-crop) image
+  const uint8_t* im = img + static_cast<size_t>(b) * H * W * 3;
+  int ymin = ry, yn = 1, xmin = rx, xn = 1;
+  if (ay.need) { ymin = ay.bounds[2 * ry]; yn = ay.bounds[2 * ry + 1]; }
+  if (ax.need) { xmin = ax.bounds[2 * rx]; xn = ax.bounds[2 * rx + 1]; }
+  int v0 = 1 << 21, v1 = 1 << 21, v2 = 1 << 21;
+  int h0 = 0, h1 = 0, h2 = 0;
+  for (int y = 0; y < yn; ++y) {
+    const uint8_t* row = im + static_cast<size_t>(ymin + y) * W * 3;
+    if (ax.need) {
+      int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+      for (int x = 0; x < xn; ++x) {
+        const int k = ax.kk[rx * ax.ksize + x];
+        const uint8_t* px = row + (xmin + x) * 3;
+        a0 += px[0] * k; a1 += px[1] * k; a2 += px[2] * k;
+      }
+      h0 = clip8_fixed(a0); h1 = clip8_fixed(a1); h2 = clip8_fixed(a2);
+    } else {
+      h0 = row[rx * 3]; h1 = row[rx * 3 + 1]; h2 = row[rx * 3 + 2];
+    }
+    if (ay.need) {
+      const int k = ay.kk[ry * ay.ksize + y];
+      v0 += h0 * k; v1 += h1 * k; v2 += h2 * k;
+    }
+  }
+  if (ay.need) { h0 = clip8_fixed(v0); h1 = clip8_fixed(v1); h2 = clip8_fixed(v2); }
+  // ToTensor (/255) and Normalize, IEEE fp32 like torch
+  const float m0 = 0.48145466f, m1 = 0.4578275f, m2 = 0.40821073f, s0 = 0.26862954f, s1 = 0.26130258f, s2 = 0.27577711f;
+  float* o = out + static_cast<size_t>(b) * 3 * size * size + static_cast<size_t>(oy) * size + ox;
+  o[0] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(h0), 255.0f), m0), s0);
+  o[static_cast<size_t>(size) * size] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(h1), 255.0f), m1), s1);
+  o[2 * static_cast<size_t>(size) * size] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(h2), 255.0f), m2), s2);
+}

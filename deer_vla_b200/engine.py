@@ -199,6 +199,43 @@ class DeerEngine:
                                             _ptr(out["exit_layer"]), _ptr(out["delta"])))
         return out
 
+    def preprocess(self, frames_u8: torch.Tensor) -> torch.Tensor:
+        """On-device open_clip image transform: CUDA uint8 [n,H,W,3] -> fp32 [n,3,S,S] (bit-exact Pillow bicubic + normalise)."""
+        assert frames_u8.is_cuda and frames_u8.dtype == torch.uint8 and frames_u8.ndim == 4 and frames_u8.shape[-1] == 3
+        f = frames_u8.contiguous()
+        n, H, W, _ = f.shape
+        out = torch.empty(n, 3, self.cfg.image_size, self.cfg.image_size, dtype=torch.float32, device=f.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self.lib.deer_preprocess_u8(self._h, _ptr(f), n, H, W, _ptr(out), C.c_void_p(stream)))
+        return out
+
+    def step_u8(self, rgb_u8: torch.Tensor, gripper_u8: torch.Tensor, ids: torch.Tensor, mask: Optional[torch.Tensor] = None,
+                slots: Optional[torch.Tensor] = None, timesteps: Optional[torch.Tensor] = None, exit_id: Optional[int] = None,
+                full_depth: bool = False) -> Dict[str, torch.Tensor]:
+        """Raw camera frames in (uint8 [n,H,W,3], HOST tensors; pinned for full speed): H2D of the uint8 frames, the image
+        transform, the step and the D2H of the results all happen inside ``deer_step_host_u8``."""
+        n, S = int(ids.shape[0]), int(ids.shape[1])
+        assert not rgb_u8.is_cuda and rgb_u8.dtype == torch.uint8 and gripper_u8.dtype == torch.uint8
+        rgb_u8, gripper_u8 = rgb_u8.contiguous(), gripper_u8.contiguous()
+        if mask is None:
+            mask = torch.ones(n, S, dtype=torch.uint8)
+        if slots is None:
+            slots = torch.arange(n, dtype=torch.int32)
+        ids, mask, slots = ids.to(torch.int64).contiguous(), mask.to(torch.uint8).contiguous(), slots.to(torch.int32).contiguous()
+        if timesteps is not None:
+            timesteps = timesteps.to(torch.int32).contiguous()
+        flags = _lib.FLAG_FULL_DEPTH if full_depth else 0
+        sx = -1 if exit_id is None else int(exit_id if exit_id >= 0 else exit_id + self.cfg.n_layers)
+        nthr = max(1, self.cfg.n_thresholds)
+        out = {"pose": self._pin("pose", (n, 6), torch.float32), "gripper": self._pin("grip", (n,), torch.float32),
+               "action": self._pin("action", (n, 7), torch.float32), "exit_layer": self._pin("exit", (n,), torch.int32),
+               "delta": self._pin("delta", (n, nthr), torch.float32)}
+        self._check(self.lib.deer_step_host_u8(self._h, n, _ptr(slots), _ptr(rgb_u8), rgb_u8.shape[1], rgb_u8.shape[2], _ptr(gripper_u8),
+                                               gripper_u8.shape[1], gripper_u8.shape[2], _ptr(ids), _ptr(mask), S, _ptr(timesteps), sx, flags,
+                                               _ptr(out["pose"]), _ptr(out["gripper"]), _ptr(out["action"]), _ptr(out["exit_layer"]),
+                                               _ptr(out["delta"])))
+        return out
+
     # ---- parity taps ------------------------------------------------------------------------------
     def get_tap(self, name: str, layer: int = 0) -> np.ndarray:
         cap = {"vit": 2 * self.max_batch * (self.cfg.image_size // self.cfg.patch) ** 2 * self.cfg.vit_width,

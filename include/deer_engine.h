@@ -170,6 +170,18 @@ typedef struct deer_profile {
 int deer_set_profile(deer_ctx* ctx, int enable);
 int deer_get_profile(deer_ctx* ctx, deer_profile* out);
 
+/* on-device image transform -- replaces preprocess_image -> open_clip image_transform for raw uint8 camera frames
+ * (data.py:898-902; eval_utils.py:292-296,317-321): torchvision Resize(image_size, BICUBIC) on a PIL image (bit-exact
+ * with Pillow's 8-bit resampler) -> CenterCrop -> /255 -> Normalize(CLIP mean/std).
+ * frames: DEVICE uint8 [n,H,W,3]; out: DEVICE fp32 [n,3,image_size,image_size]. */
+int deer_preprocess_u8(deer_ctx* ctx, const uint8_t* frames, int n, int H, int W, float* out, void* stream);
+/* deer_step_host fed with RAW camera frames (HOST uint8 [n,Hs,Ws,3] static camera, [n,Hg,Wg,3] gripper camera, e.g.
+ * CALVIN's 200x200 and 84x84): 8.5x fewer host->device bytes than normalised fp32 frames, transform on the GPU. */
+int deer_step_host_u8(deer_ctx* ctx, int n, const int32_t* slots, const uint8_t* rgb, int Hs, int Ws, const uint8_t* gripper,
+                      int Hg, int Wg, const int64_t* ids, const uint8_t* mask, int S, const int32_t* timesteps,
+                      int static_exit, uint32_t flags,
+                      float* pose_out, float* gripper_out, float* action_out, int32_t* exit_out, float* delta_out);
+
 /* introspection for parity tests (the reference exposes .hidden_states / module attributes) */
 int deer_get_state(deer_ctx* ctx, int slot, float* h_out, float* c_out);   /* HOST [layers, hidden] each */
 /* name: "vit" [2n, patches, width] (rgb images then gripper images), "media" [n, 2*latents, width],

@@ -104,3 +104,29 @@ def test_engine_fails_loudly_without_gpu():
     from deer_vla_b200.engine import DeerEngine
     with pytest.raises(DeerError, match="no CUDA device"):
         DeerEngine(config_tiny(), max_batch=1)
+
+
+def test_checkpoint_name_and_hyperparameter_readout():
+    """eval_calvin.py:356-489: configuration smuggled through the checkpoint file name + dict."""
+    from deer_vla_b200.checkpoint import config_from_checkpoint, parse_checkpoint_name, readout_args
+    name = "DeeR_task_D_D-exit-strategy-post_4+1-exit-mpt_dolly_3b-layer_11_multie_intv=2_extrae_nodth_reg_aug_10_4_traj_cons_ws_12_mpt_dolly_3b_4.pth"
+    f = parse_checkpoint_name(name)
+    assert f["llm_name"] == "mpt_dolly_3b" and f["rgb_pad"] == 10 and f["gripper_pad"] == 4 and f["traj_cons"] is True
+    assert f["multi_step_action"] == 1 and not f["use_state"] and not f["sep_resampler"] and not f["dif_ws"]
+    assert parse_checkpoint_name("x_mpt_9b_y.pth")["llm_name"] == "mpt_9b"
+    assert parse_checkpoint_name("a_3_step_b_mpt_3b.pth")["multi_step_action"] == 3
+    f2 = parse_checkpoint_name("m_difws_8_16_n.pth")
+    assert f2["dif_ws"] and f2["window_size"] == 16
+    ck = dict(head_type="deterministic", early_exit_layer=11, multi_exit=True, exit_interval=2, mlp_layernorm=True,
+              lstm_layernorm=True, mlp_num_hidden_layers=2, lstm_num_layers=4, pooling="max", dropout_mode="layerwise")
+    a = readout_args(ck, "mpt_dolly_3b", None)
+    assert a["max_layer"] == 12 and a["exit_interval"] == 2
+    old = readout_args({}, "mpt_9b", None)                  # old checkpoints: defaults; early_exit_layer -1 -> 31
+    assert old["early_exit_layer"] == 31 and old["mlp_num_hidden_layers"] == 3 and old["dropout_mode"] == "wo_last"
+    cfg = config_from_checkpoint(ck, name, max_layer=12)
+    assert cfg.exit_list == [1, 3, 5, 7, 9, 11] and cfg.n_layers == 12
+    assert config_from_checkpoint(ck, name, max_layer=4).exit_list == [1, 3, 4]
+    with pytest.raises(NotImplementedError):
+        config_from_checkpoint({}, name)                     # an old-style head (no LayerNorm, 3 hidden layers) is out of scope
+    with pytest.raises(NotImplementedError):
+        config_from_checkpoint(ck, name.replace("traj_cons", "state"))
