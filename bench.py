@@ -232,6 +232,26 @@ def engine_arm(a):
     h2d = 2 * img_bytes + B * S * 8 + B * S + B * 4
     d2h = B * (6 + 1 + 7 + 1) * 4
 
+    # ---- the same, fed with RAW camera frames (CALVIN: 200x200 static + 84x84 gripper, uint8): transform on the GPU --------
+    gen = torch.Generator().manual_seed(77 + rank)
+    u_frames = [(torch.randint(0, 256, (B, 200, 200, 3), dtype=torch.uint8, generator=gen).pin_memory(),
+                 torch.randint(0, 256, (B, 84, 84, 3), dtype=torch.uint8, generator=gen).pin_memory()) for _ in range(2)]
+    eng.reset()
+    for t in range(2):
+        eng.step_u8(u_frames[t % 2][0], u_frames[t % 2][1], h_ids, h_mask, h_slots)
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(a.steps):
+        o = eng.step_u8(u_frames[t % 2][0], u_frames[t % 2][1], h_ids, h_mask, h_slots)
+        _ = float(o["action"][0, 0])
+    barrier()
+    tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_u8 = {"value": world * B * a.steps / float(tt.item()), "unit": "action-steps/s",
+              "h2d_bytes_per_step": B * (200 * 200 + 84 * 84) * 3 + B * S * 8 + B * S + B * 4, "d2h_bytes_per_step": d2h,
+              "input": "uint8 HWC camera frames 200x200 + 84x84; Pillow-exact bicubic resize + normalise on the GPU (deer_step_host_u8)"}
+
     # ---- per-kernel profile pass: CUDA events around every GEMM launch on the launching stream ---------
     eng.set_profile(True)
     eng.reset()
@@ -305,7 +325,7 @@ def engine_arm(a):
                            "weights": "seeded synthetic (no checkpoints offline)", "calibration_samples": int(table.shape[1]),
                            "cuda_graph": bool(a.graph)},
                 "e2e": {"value": e2e_value, "unit": "action-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
+                "e2e_raw_frames": e2e_u8, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
                 "exit_histogram": {str(e): int(exit_hist[e]) for e in exits_sorted},
                 "mean_exit_depth_layers": float(sum((e + 1) * exit_hist[e] for e in exits_sorted) / max(1, total_steps)),
                 "step_algorithmic_tflops": step_tflops, "weights_load_s": t_load,
