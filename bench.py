@@ -26,15 +26,39 @@ import numpy as np   # noqa: E402
 import torch         # noqa: E402
 
 WORKLOADS = {
-    # name: (max_layer, exit_ratio, description)      README.md:124 (12 = DeeR-B, 4 = DeeR-S), README.md:110-122
-    "deer_b": (12, 1.0, "OpenFlamingo-3B DeeR-B max_layer=12 exit_ratio=1.0"),
-    "deer_s": (4, 0.8, "OpenFlamingo-3B DeeR-S max_layer=4 exit_ratio=0.8"),
+    # name: (family, max_layer, exit_ratio, description)      README.md:124 (12 = DeeR-B, 4 = DeeR-S), README.md:110-122, 311
+    "deer_b": ("3b", 12, 1.0, "OpenFlamingo-3B DeeR-B max_layer=12 exit_ratio=1.0"),
+    "deer_s": ("3b", 4, 0.8, "OpenFlamingo-3B DeeR-S max_layer=4 exit_ratio=0.8"),
+    "deer_9b": ("9b", 12, 1.0, "OpenFlamingo-9B (MPT-7B) DeeR max_layer=12 exit_ratio=1.0"),
 }
 
 
-def algorithmic_gflop_per_step(exit_layer: int, exit_rank: int) -> float:
-    """SURVEY.md §8(d) / BASELINE.md §3: 347.0 + 5.79*(e+1) + 0.082*(k+3) GFLOP for an episode exiting at E[k]=e."""
-    return 347.0 + 5.79 * (exit_layer + 1) + 0.082 * (exit_rank + 3)
+def workload(a):
+    """(family, max_layer, exit_ratio, description) with the --max-layer / --exit-ratio overrides of the C5 sweep applied."""
+    fam, ml, er, desc = WORKLOADS[a.workload]
+    if getattr(a, "max_layer", None) is not None or getattr(a, "exit_ratio", None) is not None:
+        ml = a.max_layer if a.max_layer is not None else ml
+        er = a.exit_ratio if a.exit_ratio is not None else er
+        desc = f"OpenFlamingo-{fam.upper()} DeeR max_layer={ml} exit_ratio={er}"
+    return fam, ml, er, desc
+
+
+def algorithmic_gflop_per_step(cfg, S: int, exit_layer: int, exit_rank: int) -> float:
+    """dense algorithmic FLOPs (2*MAC) of one action-step exiting at E[k]=e, from the config's dimensions.
+    For OpenFlamingo-3B, S=32 this is the survey's 347.0 + 5.79*(e+1) + 0.082*(k+3) GFLOP."""
+    w, t = cfg.vit_width, (cfg.image_size // cfg.patch) ** 2 + 1
+    vit = (t - 1) * 3 * cfg.patch ** 2 * w + cfg.vit_layers * (t * (4 * w * w + 2 * w * cfg.vit_mlp) + 2 * t * t * w)
+    inner = cfg.perc_heads * cfg.perc_dim_head
+    nk = (t - 1) + cfg.num_latents
+    perc = cfg.perc_depth * (cfg.num_latents * w * inner * 2 + nk * w * 2 * inner + 2 * cfg.num_latents * nk * inner
+                             + 2 * cfg.num_latents * w * w * cfg.perc_ff_mult)
+    d, xi, nm = cfg.d_model, cfg.xattn_heads * cfg.xattn_dim_head, 2 * cfg.num_latents
+    xattn = nm * w * 2 * xi + S * (2 * d * xi + 2 * d * d * cfg.xattn_ff_mult + 2 * nm * xi)
+    mpt = S * (4 * d * d + 2 * d * d * cfg.mlp_ratio) + 2 * S * S * d
+    layers = sum(mpt + (xattn if cfg.has_xattn(l) else 0) for l in range(exit_layer + 1))
+    H = cfg.lstm_hidden
+    head = 4 * H * (d + H) + (cfg.lstm_layers - 1) * 8 * H * H + 2 * (H * cfg.mlp_dims[0] + cfg.mlp_dims[0] * cfg.mlp_dims[1]) + 7 * cfg.mlp_dims[1]
+    return 2.0 * (2 * vit + 2 * perc + layers + (exit_rank + 3) * head) / 1e9
 
 
 class ClockSampler:
@@ -83,14 +107,17 @@ def measured_peaks():
 # ---------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's CPU path, batch 1, fp32, all host threads
 # ---------------------------------------------------------------------------------------------------
-def run_cpu_reference(workload: str, steps: int, warmup: int, S: int):
+def run_cpu_reference(wl, steps: int, warmup: int, S: int):
     from oracle import deer_oracle as O      # the one place bench.py executes oracle/: as the timed CPU baseline
-    max_layer, exit_ratio, desc = WORKLOADS[workload]
+    fam, max_layer, exit_ratio, desc = wl
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg = O.config_3b(max_layer)
+    cfg = O.config_3b(max_layer) if fam == "3b" else O.config_9b(max_layer)
     W = O.synth_weights(cfg, 0)
     gold = np.load(os.path.join(ROOT, "tests", "golden", "full3b.npz"))
-    thr = gold["thresholds_B" if workload == "deer_b" else "thresholds_S"].tolist()
+    if fam == "3b" and max_layer in (12, 4):
+        thr, thr_desc = gold["thresholds_B" if max_layer == 12 else "thresholds_S"].tolist(), "golden thresholds"
+    else:                     # no committed calibration for this config: run every step to the deepest controlled exit
+        thr, thr_desc = [-1e8] * (cfg.n_thresholds - 1) + [1e8], "thresholds forcing the deepest exit"
     orc = O.DeerOracle(cfg, W, thr)
     orc.reset()
     ids = O.synth_tokens(cfg, 0, S)
@@ -105,15 +132,15 @@ def run_cpu_reference(workload: str, steps: int, warmup: int, S: int):
     dt = time.perf_counter() - t0
     return {"value": steps / dt, "ms_per_step": 1e3 * dt / steps, "cores": torch.get_num_threads(), "exits": exits,
             "sample": f"{steps} consecutive batch-1 action-steps of one episode ({desc}, S={S}, fp32 eager, "
-                      f"carried LSTM state, golden thresholds), {warmup} warm-up"}
+                      f"carried LSTM state, {thr_desc}), {warmup} warm-up"}
 
 
 def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    max_layer, exit_ratio, desc = WORKLOADS[a.workload]
-    r = run_cpu_reference(a.workload, a.steps, a.warmup, a.seq)
+    fam, max_layer, exit_ratio, desc = workload(a)
+    r = run_cpu_reference(workload(a), a.steps, a.warmup, a.seq)
     line = {"impl": "reference", "metric": "action-steps/sec", "value": r["value"], "unit": "action-steps/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -131,10 +158,10 @@ def reference_arm(a):
 # ---------------------------------------------------------------------------------------------------
 def engine_arm(a):
     import torch.distributed as dist
-    from deer_vla_b200 import config_3b
+    from deer_vla_b200 import config_3b, config_9b
     from deer_vla_b200.engine import DeerEngine
     from deer_vla_b200.value_net import ExitController
-    from deer_vla_b200.weights import synth_frames, synth_instruction_ids, synth_state_dict
+    from deer_vla_b200.weights import synth_frames, synth_instruction_ids, synth_state_items
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -143,12 +170,12 @@ def engine_arm(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    max_layer, exit_ratio, desc = WORKLOADS[a.workload]
-    cfg = config_3b(max_layer)
+    fam, max_layer, exit_ratio, desc = workload(a)
+    cfg = config_3b(max_layer) if fam == "3b" else config_9b(max_layer)
     B, S = a.batch, a.seq
     eng = DeerEngine(cfg, max_batch=B, max_slots=B, max_seq=S, device=local, precision="bf16", gemm_impl="tcgen05", use_graph=a.graph)
     t0 = time.time()
-    eng.load_state_dict(synth_state_dict(cfg, 0))
+    eng.load_state_dict(synth_state_items(cfg, 0))
     t_load = time.time() - t0
 
     # synthetic inputs: NF distinct frame sets per camera (each step's input set is 2*B*3*224*224*4 B = 270 MB at B=224,
@@ -296,7 +323,7 @@ def engine_arm(a):
 
     # whole-step algorithmic FLOP rate from the measured exit histogram (SURVEY §8d formula)
     exits_sorted = [e for e in cfg.exit_list if e <= cfg.ctrl_max_layer]
-    total_gflop = sum(int(exit_hist[e]) * algorithmic_gflop_per_step(e, exits_sorted.index(e)) for e in exits_sorted)
+    total_gflop = sum(int(exit_hist[e]) * algorithmic_gflop_per_step(cfg, S, e, exits_sorted.index(e)) for e in exits_sorted)
     total_steps = int(exit_hist.sum())
     step_tflops = (total_gflop / 1e3) / (ms / 1e3) if ms > 0 else 0.0
 
@@ -313,7 +340,7 @@ def engine_arm(a):
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         eng.close()
         torch.cuda.empty_cache()
-        r = run_cpu_reference(a.workload, a.cpu_steps, 1, S)
+        r = run_cpu_reference(workload(a), a.cpu_steps, 1, S)
         cpu_base = {"value": r["value"], "unit": "action-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     if rank == 0:
         line = {"metric": "action-steps/sec", "value": value, "unit": "action-steps/s", "n_gpus": world, "steps": a.steps,
@@ -343,6 +370,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--workload", default="deer_b", choices=list(WORKLOADS))
+    ap.add_argument("--max-layer", type=int, default=None, help="override the workload's max_layer (C5 sweep)")
+    ap.add_argument("--exit-ratio", type=float, default=None, help="override the workload's exit_ratio (C5 sweep)")
     ap.add_argument("--batch", type=int, default=224, help="concurrent episodes per GPU")
     ap.add_argument("--seq", type=int, default=32)
     ap.add_argument("--calib-steps", type=int, default=8)

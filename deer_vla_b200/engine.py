@@ -118,7 +118,7 @@ class DeerEngine:
         """Accepts the reference's state-dict keys (optionally 'module.'-prefixed, train_utils.py:631-638);
         tensors not on the hot path are skipped like the reference's strict=False loads (eval_calvin.py:543,577)."""
         used = 0
-        for name, t in sd.items():
+        for name, t in (sd.items() if hasattr(sd, "items") else sd):
             if isinstance(t, torch.Tensor):
                 a = t.detach().to(torch.float32).cpu().contiguous().numpy()
             else:

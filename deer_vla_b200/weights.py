@@ -92,7 +92,12 @@ _GATES = [0.5, -0.4, 0.7, 0.35, -0.6, 0.45]
 
 
 def synth_state_dict(cfg: DeerConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
-    out: Dict[str, torch.Tensor] = {}
+    return dict(synth_state_items(cfg, seed))
+
+
+def synth_state_items(cfg: DeerConfig, seed: int = 0):
+    """Generator form of ``synth_state_dict``: one (name, tensor) at a time, so loading a replica never holds the whole
+    fp32 state dict (6 GB for the 3B model) in host memory -- N ranks on one box load concurrently."""
     gi = 0
     for idx, (name, shape, kind) in enumerate(state_dict_spec(cfg)):
         g = torch.Generator().manual_seed(seed * 1000003 + zlib.crc32(name.encode()))
@@ -115,8 +120,7 @@ def synth_state_dict(cfg: DeerConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
             gi += 1
         else:
             raise ValueError(kind)
-        out[name] = t.float().contiguous()
-    return out
+        yield name, t.float().contiguous()
 
 
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
