@@ -304,6 +304,8 @@ struct deer_ctx {
   int tap_n = 0, tap_S = 0;
   int vit_chunk = 0;           // images per ViT pass (0 = all at once); DEER_VIT_CHUNK overrides
   cudaStream_t own_stream = nullptr;
+  // cross-stream ordering of consecutive calls on one ctx (workspace and episode state are shared)
+  cudaEvent_t last_done = nullptr; cudaStream_t last_stream = nullptr; bool has_last = false;
   int* nact_hist = nullptr;            // device [16]: active count after each probe of the last step
   int n_probes_last = 0, n_last = 0;
   cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
@@ -546,6 +548,7 @@ extern "C" int deer_create(const deer_config* cfg, int device, deer_ctx** out) {
 #undef WS
   if (cudaMallocHost(&c->h_nact, 4) != cudaSuccess) { set_err(&c->err, DEER_E_CUDA, "cudaMallocHost failed"); g_last_error = c->err; deer_destroy(c); return DEER_E_CUDA; }
   cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->last_done, cudaEventDisableTiming);
   // ALiBi slopes (MPT attention.alibi_bias / gen_slopes): 2^-(i * bias_max / Hp), interleaved when H is not a power of two
   {
     const int Hn = f.n_heads;
@@ -580,6 +583,7 @@ extern "C" void deer_destroy(deer_ctx* c) {
   if (c->ev_step0) cudaEventDestroy(c->ev_step0);
   if (c->ev_step1) cudaEventDestroy(c->ev_step1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->last_done) cudaEventDestroy(c->last_done);
   for (auto& kv : c->graphs) { if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec); if (kv.second.graph) cudaGraphDestroy(kv.second.graph); }
   for (auto s2 : c->cap_streams) if (s2) cudaStreamDestroy(s2);
   for (int k = 0; k < 2; ++k) if (c->u8_stage[k]) cudaFree(c->u8_stage[k]);
@@ -795,28 +799,45 @@ extern "C" int deer_set_thresholds(deer_ctx* c, const float* thr, int n) {
   if (!c || !thr) return set_err(c ? &c->err : nullptr, DEER_E_INVALID, "null argument");
   if (n != c->n_thr) return set_err(&c->err, DEER_E_INVALID, "got %d thresholds, expected %d (value_net.py:178-179)", n, c->n_thr);
   cudaSetDevice(c->device);
+  if (c->has_last) CK(cudaStreamSynchronize(c->last_stream));     // a step still in flight reads the old thresholds
   CK(cudaMemcpy(c->thr_dev, thr, n * 4, cudaMemcpyHostToDevice));
   c->thresholds_set = true;
   return DEER_OK;
+}
+
+// Calls on one ctx may arrive on different streams (caller's stream for deer_step, the engine's own stream for the
+// host-buffer entry points, per-subtask resets in between).  The workspace and the per-slot state are shared, so every
+// call is ordered after the previous one with an event instead of relying on the caller to synchronise.
+static void order_after_last(deer_ctx* c, cudaStream_t st) {
+  if (c->has_last && c->last_stream != st) cudaStreamWaitEvent(st, c->last_done, 0);
+}
+static void mark_done(deer_ctx* c, cudaStream_t st) {
+  cudaEventRecord(c->last_done, st);
+  c->last_stream = st; c->has_last = true;
 }
 
 extern "C" int deer_reset(deer_ctx* c, const int32_t* slots, int n) {
   if (!c) return set_err(nullptr, DEER_E_INVALID, "null ctx");
   cudaSetDevice(c->device);
   const size_t per = (size_t)c->cfg.lstm_layers * c->cfg.lstm_hidden * 4;
+  // stream-ordered after the last step (wherever it ran); before any step, on the engine's own stream
+  cudaStream_t st = c->has_last ? c->last_stream : c->own_stream;
   if (n < 0) {
-    CK(cudaMemset(c->h_state, 0, per * c->cfg.max_slots));
-    CK(cudaMemset(c->c_state, 0, per * c->cfg.max_slots));
-    CK(cudaMemset(c->cur_exit_id, 0, 4 * (size_t)c->cfg.max_slots));
+    CK(cudaMemsetAsync(c->h_state, 0, per * c->cfg.max_slots, st));
+    CK(cudaMemsetAsync(c->c_state, 0, per * c->cfg.max_slots, st));
+    CK(cudaMemsetAsync(c->cur_exit_id, 0, 4 * (size_t)c->cfg.max_slots, st));
+    mark_done(c, st);
     return DEER_OK;
   }
   if (!slots) return set_err(&c->err, DEER_E_INVALID, "null slots");
-  for (int i = 0; i < n; ++i) {
+  for (int i = 0; i < n; ++i)
     if (slots[i] < 0 || slots[i] >= c->cfg.max_slots) return set_err(&c->err, DEER_E_INVALID, "slot %d out of range", slots[i]);
-    CK(cudaMemset(reinterpret_cast<char*>(c->h_state) + per * slots[i], 0, per));
-    CK(cudaMemset(reinterpret_cast<char*>(c->c_state) + per * slots[i], 0, per));
-    CK(cudaMemset(c->cur_exit_id + slots[i], 0, 4));
+  for (int i = 0; i < n; ++i) {
+    CK(cudaMemsetAsync(reinterpret_cast<char*>(c->h_state) + per * slots[i], 0, per, st));
+    CK(cudaMemsetAsync(reinterpret_cast<char*>(c->c_state) + per * slots[i], 0, per, st));
+    CK(cudaMemsetAsync(c->cur_exit_id + slots[i], 0, 4, st));
   }
+  mark_done(c, st);
   return DEER_OK;
 }
 
@@ -1208,11 +1229,13 @@ extern "C" int deer_step(deer_ctx* c, int n, const int32_t* slots, const float* 
   cudaSetDevice(c->device);
   c->stats.step = 0; c->stats.gemm_step = 0; c->stats.gemm_flops_step = 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  order_after_last(c, st);
   int r;
   if (c->cfg.use_graph && !c->cfg.host_control && !c->gemm.profile)
     r = step_graph(c, n, slots, rgb, gripper, ids, mask, S, timesteps, static_exit, flags, pose_out, gripper_out, action_out, exit_out, delta_out, st);
   else
     r = step_dispatch(c, n, slots, rgb, gripper, ids, mask, S, timesteps, static_exit, flags, pose_out, gripper_out, action_out, exit_out, delta_out, st);
+  mark_done(c, st);
   if (r == DEER_OK) c->steps++;
   return r;
 }

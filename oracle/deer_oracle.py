@@ -32,6 +32,39 @@ import torch.nn.functional as F
 
 Tensor = torch.Tensor
 
+# Rounding yardstick: with OPERAND_DTYPE = torch.bfloat16 both operands of every contraction
+# (linear, conv patch-embed, QK^T, PV) are rounded to bf16 and accumulated in fp32 -- what ANY bf16 tensor-core forward
+# does -- while everything else stays fp32.  |this - fp32| is the size of "bf16 tolerance" for a given model and input;
+# the tests require the engine's bf16 path to sit inside a small multiple of it.  None = the plain fp32 reference.
+OPERAND_DTYPE = None
+
+
+class operand_rounding:
+    """``with operand_rounding(torch.bfloat16): ...`` -- context manager for OPERAND_DTYPE."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global OPERAND_DTYPE
+        self.prev, OPERAND_DTYPE = OPERAND_DTYPE, self.dtype
+
+    def __exit__(self, *exc):
+        global OPERAND_DTYPE
+        OPERAND_DTYPE = self.prev
+
+
+def _r(x: Tensor) -> Tensor:
+    return x if OPERAND_DTYPE is None else x.to(OPERAND_DTYPE).to(torch.float32)
+
+
+def _linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None) -> Tensor:
+    return F.linear(_r(x), _r(w), b)
+
+
+def _mm(a: Tensor, b: Tensor) -> Tensor:
+    return torch.matmul(_r(a), _r(b))
+
 
 # --------------------------------------------------------------------------------------
 # configuration
@@ -297,7 +330,7 @@ def vit_forward(cfg: DeerConfig, W: Dict[str, Tensor], images: Tensor) -> Tensor
     """
     p = "vision_encoder.visual."
     N = images.shape[0]
-    x = F.conv2d(images, W[p + "conv1.weight"], None, stride=cfg.patch)           # (N,width,g,g)
+    x = F.conv2d(_r(images), _r(W[p + "conv1.weight"]), None, stride=cfg.patch)           # (N,width,g,g)
     x = x.reshape(N, cfg.vit_width, -1).permute(0, 2, 1)                          # (N,g*g,width)
     cls = W[p + "class_embedding"].view(1, 1, -1).expand(N, 1, -1)
     x = torch.cat([cls, x], dim=1) + W[p + "positional_embedding"]
@@ -306,18 +339,18 @@ def vit_forward(cfg: DeerConfig, W: Dict[str, Tensor], images: Tensor) -> Tensor
     for i in range(cfg.vit_layers):
         q_ = f"{p}transformer.resblocks.{i}."
         a = _ln(x, W[q_ + "ln_1.weight"], W[q_ + "ln_1.bias"])
-        qkv = F.linear(a, W[q_ + "attn.in_proj_weight"], W[q_ + "attn.in_proj_bias"])
+        qkv = _linear(a, W[q_ + "attn.in_proj_weight"], W[q_ + "attn.in_proj_bias"])
         q, k, v = qkv.chunk(3, dim=-1)
         q = q.view(N, -1, H, hd).transpose(1, 2) * (hd ** -0.5)    # nn.MultiheadAttention scales q
         k = k.view(N, -1, H, hd).transpose(1, 2)
         v = v.view(N, -1, H, hd).transpose(1, 2)
-        att = torch.softmax(q @ k.transpose(-1, -2), dim=-1)
-        o = (att @ v).transpose(1, 2).reshape(N, -1, cfg.vit_width)
-        x = x + F.linear(o, W[q_ + "attn.out_proj.weight"], W[q_ + "attn.out_proj.bias"])
+        att = torch.softmax(_mm(q, k.transpose(-1, -2)), dim=-1)
+        o = _mm(att, v).transpose(1, 2).reshape(N, -1, cfg.vit_width)
+        x = x + _linear(o, W[q_ + "attn.out_proj.weight"], W[q_ + "attn.out_proj.bias"])
         m = _ln(x, W[q_ + "ln_2.weight"], W[q_ + "ln_2.bias"])
-        h = F.linear(m, W[q_ + "mlp.c_fc.weight"], W[q_ + "mlp.c_fc.bias"])
+        h = _linear(m, W[q_ + "mlp.c_fc.weight"], W[q_ + "mlp.c_fc.bias"])
         h = h * torch.sigmoid(1.702 * h)                                             # QuickGELU
-        x = x + F.linear(h, W[q_ + "mlp.c_proj.weight"], W[q_ + "mlp.c_proj.bias"])
+        x = x + _linear(h, W[q_ + "mlp.c_proj.weight"], W[q_ + "mlp.c_proj.bias"])
     return x[:, 1:]
 
 
@@ -335,19 +368,19 @@ def perceiver_forward(cfg: DeerConfig, W: Dict[str, Tensor], feats: Tensor, pref
         p = f"{prefix}layers.{i}."
         xm = _ln(feats, W[p + "0.norm_media.weight"], W[p + "0.norm_media.bias"])
         ln_lat = _ln(lat, W[p + "0.norm_latents.weight"], W[p + "0.norm_latents.bias"])
-        q = F.linear(ln_lat, W[p + "0.to_q.weight"])
+        q = _linear(ln_lat, W[p + "0.to_q.weight"])
         kv_in = torch.cat([xm, ln_lat], dim=-2)                                     # helpers.py:53
-        k, v = F.linear(kv_in, W[p + "0.to_kv.weight"]).chunk(2, dim=-1)
+        k, v = _linear(kv_in, W[p + "0.to_kv.weight"]).chunk(2, dim=-1)
         q = q.view(N, -1, h, dh).transpose(1, 2) * (dh ** -0.5)
         k = k.view(N, -1, h, dh).transpose(1, 2)
         v = v.view(N, -1, h, dh).transpose(1, 2)
-        sim = q @ k.transpose(-1, -2)
+        sim = _mm(q, k.transpose(-1, -2))
         sim = sim - sim.amax(dim=-1, keepdim=True)                                   # helpers.py:60
         att = sim.softmax(dim=-1)
-        o = (att @ v).transpose(1, 2).reshape(N, -1, h * dh)
-        lat = F.linear(o, W[p + "0.to_out.weight"]) + lat                           # helpers.py:130
+        o = _mm(att, v).transpose(1, 2).reshape(N, -1, h * dh)
+        lat = _linear(o, W[p + "0.to_out.weight"]) + lat                           # helpers.py:130
         f = _ln(lat, W[p + "1.0.weight"], W[p + "1.0.bias"])
-        f = F.linear(F.gelu(F.linear(f, W[p + "1.1.weight"])), W[p + "1.3.weight"])
+        f = _linear(F.gelu(_linear(f, W[p + "1.1.weight"])), W[p + "1.3.weight"])
         lat = f + lat                                                                # helpers.py:131
     return _ln(lat, W[prefix + "norm.weight"], W[prefix + "norm.bias"])
 
@@ -375,12 +408,12 @@ def gated_xattn_forward(cfg: DeerConfig, W: Dict[str, Tensor], layer: int, x: Te
     B, S, _ = x.shape
     h, dh = cfg.xattn_heads, cfg.xattn_dim_head
     xn = _ln(x, W[p + "attn.norm.weight"], W[p + "attn.norm.bias"])
-    q = F.linear(xn, W[p + "attn.to_q.weight"])
-    k, v = F.linear(media, W[p + "attn.to_kv.weight"]).chunk(2, dim=-1)
+    q = _linear(xn, W[p + "attn.to_q.weight"])
+    k, v = _linear(media, W[p + "attn.to_kv.weight"]).chunk(2, dim=-1)
     q = q.view(B, S, h, dh).transpose(1, 2) * (dh ** -0.5)
     k = k.view(B, -1, h, dh).transpose(1, 2)
     v = v.view(B, -1, h, dh).transpose(1, 2)
-    sim = q @ k.transpose(-1, -2)                                                    # (B,h,S,n)
+    sim = _mm(q, k.transpose(-1, -2))                                                    # (B,h,S,n)
     text_time = media_locations.cumsum(dim=-1)                                       # helpers.py:208
     media_time = torch.ones(media.shape[1], dtype=text_time.dtype)                   # T_img=1 -> all latents time 1
     mask = text_time.view(B, 1, S, 1) == media_time.view(1, 1, 1, -1)                # helpers.py:214-218
@@ -388,10 +421,10 @@ def gated_xattn_forward(cfg: DeerConfig, W: Dict[str, Tensor], layer: int, x: Te
     sim = sim - sim.amax(dim=-1, keepdim=True)
     att = sim.softmax(dim=-1)
     att = att.masked_fill((text_time == 0).view(B, 1, S, 1), 0.0)                    # helpers.py:223-229
-    o = (att @ v).transpose(1, 2).reshape(B, S, h * dh)
-    x = F.linear(o, W[p + "attn.to_out.weight"]) * torch.tanh(W[p + "attn_gate"]) + x
+    o = _mm(att, v).transpose(1, 2).reshape(B, S, h * dh)
+    x = _linear(o, W[p + "attn.to_out.weight"]) * torch.tanh(W[p + "attn_gate"]) + x
     f = _ln(x, W[p + "ff.0.weight"], W[p + "ff.0.bias"])
-    f = F.linear(F.gelu(F.linear(f, W[p + "ff.1.weight"])), W[p + "ff.3.weight"])
+    f = _linear(F.gelu(_linear(f, W[p + "ff.1.weight"])), W[p + "ff.3.weight"])
     return f * torch.tanh(W[p + "ff_gate"]) + x
 
 
@@ -429,7 +462,7 @@ def mpt_block_forward(cfg: DeerConfig, W: Dict[str, Tensor], layer: int, x: Tens
     n1, n2 = ("ln_1", "ln_2") if cfg.qk_ln else ("norm_1", "norm_2")
     up, down = ("mlp.mlp_up", "mlp.mlp_down") if cfg.qk_ln else ("ffn.up_proj", "ffn.down_proj")
     a = _ln(x, W[p + n1 + ".weight"], None)
-    q, k, v = F.linear(a, W[p + "attn.Wqkv.weight"]).chunk(3, dim=2)
+    q, k, v = _linear(a, W[p + "attn.Wqkv.weight"]).chunk(3, dim=2)
     if cfg.qk_ln:
         q = _ln(q, W[p + "attn.q_ln.weight"], None)
         k = _ln(k, W[p + "attn.k_ln.weight"], None)
@@ -437,15 +470,15 @@ def mpt_block_forward(cfg: DeerConfig, W: Dict[str, Tensor], layer: int, x: Tens
     k = k.view(B, S, H, hd).transpose(1, 2)
     v = v.view(B, S, H, hd).transpose(1, 2)
     min_val = torch.finfo(x.dtype).min
-    w = q @ k.transpose(-1, -2) * (1.0 / math.sqrt(hd))
+    w = _mm(q, k.transpose(-1, -2)) * (1.0 / math.sqrt(hd))
     w = w + attn_bias
     causal = ~torch.ones(S, S, dtype=torch.bool).tril()
     w = w.masked_fill(causal.view(1, 1, S, S), min_val)
     w = torch.softmax(w, dim=-1)
-    o = (w @ v).transpose(1, 2).reshape(B, S, D)
-    x = x + F.linear(o, W[p + "attn.out_proj.weight"])
+    o = _mm(w, v).transpose(1, 2).reshape(B, S, D)
+    x = x + _linear(o, W[p + "attn.out_proj.weight"])
     m = _ln(x, W[p + n2 + ".weight"], None)
-    n = F.linear(F.gelu(F.linear(m, W[p + up + ".weight"])), W[p + down + ".weight"])
+    n = _linear(F.gelu(_linear(m, W[p + up + ".weight"])), W[p + down + ".weight"])
     return x + n
 
 
@@ -462,7 +495,7 @@ def flamingo_layer_forward(cfg, W, layer, x, media, media_locations, attn_bias) 
 # --------------------------------------------------------------------------------------
 def lstm_cell(x: Tensor, h: Tensor, c: Tensor, w_ih, w_hh, b_ih, b_hh) -> Tuple[Tensor, Tensor]:
     """One step of torch.nn.LSTM (gate order i,f,g,o)."""
-    gates = F.linear(x, w_ih, b_ih) + F.linear(h, w_hh, b_hh)
+    gates = _linear(x, w_ih, b_ih) + _linear(h, w_hh, b_hh)
     i, f, g, o = gates.chunk(4, dim=-1)
     c2 = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
     h2 = torch.sigmoid(o) * torch.tanh(c2)
@@ -504,10 +537,10 @@ def head_forward(cfg: DeerConfig, W: Dict[str, Tensor], feat: Tensor, state: Opt
         y = x
         for j in range(len(cfg.mlp_dims)):
             p = f"{prefix}{head}.mlp."
-            y = F.linear(y, W[p + f"{4 * j + 1}.weight"], W[p + f"{4 * j + 1}.bias"])
+            y = _linear(y, W[p + f"{4 * j + 1}.weight"], W[p + f"{4 * j + 1}.bias"])
             y = torch.relu(_ln(y, W[p + f"{4 * j + 2}.weight"], W[p + f"{4 * j + 2}.bias"]))
         k = 4 * len(cfg.mlp_dims) + 1
-        y = F.linear(y, W[f"{prefix}{head}.mlp.{k}.weight"], W[f"{prefix}{head}.mlp.{k}.bias"])
+        y = _linear(y, W[f"{prefix}{head}.mlp.{k}.weight"], W[f"{prefix}{head}.mlp.{k}.bias"])
         outs.append(torch.tanh(y) if head == "actions" else torch.sigmoid(y))
     return outs[0], outs[1], pooled, (torch.stack(hs), torch.stack(cs))
 

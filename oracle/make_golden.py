@@ -354,13 +354,46 @@ def golden_full(S=32):
     np.savez_compressed(os.path.join(GOLD, "full3b.npz"), **out)
 
 
+def golden_yardstick(S=32, T=2):
+    """Rounding yardstick at OpenFlamingo-3B size: the oracle in fp32 and with bf16-rounded
+    contraction operands on the same inputs, full depth (every exit probed), 2 episodes x T steps -> yardstick3b.npz."""
+    torch.set_num_threads(os.cpu_count())
+    cfg = O.config_3b(12)
+    W = O.synth_weights(cfg, 0)
+    thr = [1e8] * cfg.n_thresholds
+    out = {"S": S, "T": T}
+    for mode, tag in ((None, "fp32"), (torch.bfloat16, "bf16ops")):
+        with O.operand_rounding(mode):
+            for e in (0, 1):
+                orc = O.DeerOracle(cfg, W, thr)
+                orc.reset()
+                ids = O.synth_tokens(cfg, e, S)
+                poses, grips, deltas = [], [], []
+                for t in range(T):
+                    o = orc.step(O.synth_image(cfg, e, t, 0), O.synth_image(cfg, e, t, 1), ids, full_depth=True)
+                    poses.append(o.pose.flatten().numpy()); grips.append(float(o.gripper.flatten()[0]))
+                    deltas.append(np.array([float(o.deltas[k]) for k in sorted(o.deltas)], np.float32))
+                out[f"{tag}_ep{e}_pose"] = np.stack(poses)
+                out[f"{tag}_ep{e}_gripper"] = np.array(grips, np.float32)
+                out[f"{tag}_ep{e}_deltas"] = np.stack(deltas)
+    for e in (0, 1):
+        print(f"[yardstick] ep{e}: |bf16ops - fp32| pose {np.abs(out[f'bf16ops_ep{e}_pose'] - out[f'fp32_ep{e}_pose']).max():.3e} "
+              f"deltas {np.abs(out[f'bf16ops_ep{e}_deltas'] - out[f'fp32_ep{e}_deltas']).max():.3e}")
+    np.savez_compressed(os.path.join(GOLD, "yardstick3b.npz"), **out)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
+    ap.add_argument("--yardstick-only", action="store_true")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
+    if a.yardstick_only:
+        golden_yardstick()
+        sys.exit(0)
     golden_thresholds()
     xcheck_third_party()
     golden_tiny()
     if a.full:
         golden_full()
+        golden_yardstick()

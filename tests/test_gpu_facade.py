@@ -120,3 +120,34 @@ def test_host_path_equals_device_path_and_profile():
     st = eng.stats()
     assert st.kernel_launches_last_step > 50 and st.gemm_launches_last_step > 20
     eng.close()
+
+
+def test_calls_on_different_streams_are_ordered():
+    """deer_step on the caller's stream, deer_reset, deer_step_host on the engine's stream and a side stream, back to back
+    WITHOUT host synchronisation in between: the ctx orders them itself (shared workspace / episode state)."""
+    ocfg, W, eng, model, ctrl = _build(max_batch=2)
+    eng.set_thresholds([0.3, 0.25, 1e8])
+    rgb = torch.stack([O.synth_image(ocfg, e, 0, 0) for e in (0, 1)])
+    grip = torch.stack([O.synth_image(ocfg, e, 0, 1) for e in (0, 1)])
+    ids = torch.stack([O.synth_tokens(ocfg, e, 16) for e in (0, 1)])
+    drgb, dgrip, dids = rgb.cuda(), grip.cuda(), ids.cuda()
+    hrgb, hgrip, hids = rgb.pin_memory(), grip.pin_memory(), ids.pin_memory()
+    torch.cuda.synchronize()
+    eng.reset()
+    want = eng.step(hrgb, hgrip, hids)
+    want = {k: v.clone() for k, v in want.items()}
+    side = torch.cuda.Stream()
+    for rep in range(6):
+        eng.reset()
+        d = eng.step(drgb, dgrip, dids)                       # async on the current stream
+        eng.reset()
+        h = eng.step(hrgb, hgrip, hids)                       # engine's own stream, while d may still be running
+        h = {k: v.clone() for k, v in h.items()}
+        eng.reset()
+        with torch.cuda.stream(side):
+            s2 = eng.step(drgb, dgrip, dids)                  # a third stream
+        torch.cuda.synchronize()
+        for got in (d, h, s2):
+            assert torch.equal(got["exit_layer"].cpu(), want["exit_layer"]), rep
+            assert torch.equal(got["action"].cpu(), want["action"]), rep
+    eng.close()

@@ -7,8 +7,13 @@ Tolerances (stated per test):
     layers cannot meet 1e-3 absolute on tanh outputs against an fp32 oracle, so the test states what
     it measures: pose within 5e-2 abs of the fp32 oracle (measured worst case 3.0e-2 at 3B size, 1e-2
     typical), and exit indices identical on every sample whose |delta - T| margin exceeds 0.02
-    (decisions inside the margin are rounding, not logic).
+    (decisions inside the margin are rounding, not logic).  The size of "bf16 tolerance" itself is
+    measured, not assumed: tests/golden/yardstick3b.npz holds the oracle run with bf16-rounded
+    contraction operands (Y = 1.4e-2..1.8e-2 on poses vs the fp32 oracle at 3B size), and the engine
+    must stay within 3*Y of both oracles (test_full3b_bf16_within_rounding_yardstick).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -308,6 +313,30 @@ def test_full3b_bf16_vs_reference_golden(full3b, gold_full):
             n_margin_ok += int(margin > 0.02)
     assert worst_pose <= 5e-2, worst_pose
     print(f"\n[full3b bf16] worst pose |err| {worst_pose:.3e} over {n_dec} decisions ({n_margin_ok} outside the 0.02 margin)")
+    eng.close()
+
+
+def test_full3b_bf16_within_rounding_yardstick(full3b):
+    """'bf16 tolerance' made concrete: the oracle with bf16-rounded contraction operands (fp32
+    accumulate, everything else fp32) differs from the fp32 oracle by Y on these inputs; the engine's bf16 path must be
+    within 3*Y of the fp32 oracle and within 3*Y of the bf16-operand oracle, on poses and on the gate's deltas."""
+    ocfg, W = full3b
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "yardstick3b.npz"))
+    S, T = int(g["S"]), int(g["T"])
+    eng = _engine(ocfg, W, max_batch=2, max_seq=S, precision="bf16", gemm_impl="tcgen05")
+    eng.set_thresholds([1e8] * ocfg.n_thresholds)
+    eng.reset()
+    for t in range(T):
+        rgb, grip, ids = _inputs(ocfg, [0, 1], t, S)
+        out = eng.step(rgb.cuda(), grip.cuda(), ids.cuda(), full_depth=True)
+        pose, delta = out["pose"].cpu().numpy(), out["delta"].cpu().numpy()
+        for e in range(2):
+            for name, got in (("pose", pose[e]), ("deltas", delta[e])):
+                f32, b16 = g[f"fp32_ep{e}_{name}"][t], g[f"bf16ops_ep{e}_{name}"][t]
+                yard = float(np.abs(b16 - f32).max())
+                err32, err16 = float(np.abs(got - f32).max()), float(np.abs(got - b16).max())
+                print(f"\n[yardstick] ep{e} t{t} {name}: Y={yard:.3e} |engine-fp32|={err32:.3e} |engine-bf16ops|={err16:.3e}")
+                assert err32 <= 3 * yard + 2e-3 and err16 <= 3 * yard + 2e-3, (e, t, name, yard, err32, err16)
     eng.close()
 
 
