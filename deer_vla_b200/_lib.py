@@ -75,6 +75,8 @@ SYMBOLS = {
     "deer_op_pv_probe": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "deer_op_attention": (C.c_int, [C.c_int, C.c_int, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "deer_op_attention_masked": (C.c_int, [C.c_int, C.c_int, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -433,3 +433,140 @@ flash_attn_hd64_kernel(const bf16* __restrict__ Qg, int ldq, const bf16* __restr
     if (r1 < Sq) *reinterpret_cast<uint32_t*>(O + static_cast<size_t>(r1) * ldo + col) = pack_bf16x2(o[n][2] * i1, o[n][3] * i1);
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// attn_llm_mma_kernel<HD>: bf16 tensor-core (mma.sync m16n8k16) version of the LLM-side attentions -- gated x-attn
+// (Sq<=32 text rows x 128 latents, head_dim 64) and MPT self-attention (S<=32, head_dim 128) -- with the full mask / bias
+// semantics of attn_small_kernel (ALiBi key bias, causal, key padding, x-attn media classes, dynamic batch).
+// One CTA of 2 warps per (episode, head); warp w owns query rows 16w..16w+15.  Q/K/V are staged ONCE in shared memory as
+// bf16 (cp.async, XOR-swizzled rows; 36 KB for x-attn instead of 75 KB fp32 -> 6 CTAs/SM), all Sk<=128 scores of a row
+// live in registers, so the softmax is single-pass (no online rescale).  These launches are HBM/L2-latency bound (88 MB of
+// q/k/v per launch at B=224): the point is bytes and occupancy, not FLOPs.
+// ---------------------------------------------------------------------------------------------
+template <int HD> __device__ __forceinline__ int swz_hd(int row, int col) {
+  return row * HD + (((((col >> 3) ^ (row & 7)) & 7) | ((col >> 3) & ~7)) << 3 | (col & 7));
+}
+template <int HD>
+__device__ __forceinline__ void llm_load_rows(bf16* s, const bf16* g, int ld, int nrows_pad, int nrows, int tid) {
+  constexpr int CH = HD / 8;                                  // 16-byte chunks per row
+  for (int c = tid; c < nrows_pad * CH; c += 64) {
+    const int r = c / CH, ch = c % CH;
+    const bool ok = r < nrows;
+    cp_async16(s + swz_hd<HD>(r, ch * 8), g + static_cast<size_t>(ok ? r : 0) * ld + ch * 8, ok);
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(64)
+attn_llm_mma_kernel(AttnParams p) {
+  extern __shared__ __align__(128) uint8_t smraw[];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int nb = p.n_dev ? min(*p.n_dev, p.B_host) : p.B_host;
+  if (b >= nb) return;
+  const int Sq = p.Sq, Sk = p.Sk;
+  const int skp = (Sk + 15) & ~15;                            // keys padded to the 16-key MMA granule (zero rows)
+  bf16* sQ = reinterpret_cast<bf16*>(smraw);                  // [32][HD]
+  bf16* sK = sQ + 32 * HD;                                    // [skp][HD]
+  bf16* sV = sK + skp * HD;                                   // [skp][HD]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bf16* Q = reinterpret_cast<const bf16*>(p.Q) + static_cast<size_t>(b) * Sq * p.ldq + h * HD;
+  const bf16* K = reinterpret_cast<const bf16*>(p.K) + static_cast<size_t>(b) * Sk * p.ldk + h * HD;
+  const bf16* V = reinterpret_cast<const bf16*>(p.V) + static_cast<size_t>(b) * Sk * p.ldv + h * HD;
+  bf16* O = reinterpret_cast<bf16*>(p.O) + static_cast<size_t>(b) * Sq * p.ldo + h * HD;
+  llm_load_rows<HD>(sQ, Q, p.ldq, 32, Sq, tid);
+  llm_load_rows<HD>(sK, K, p.ldk, skp, Sk, tid);
+  cp_async_commit();
+  llm_load_rows<HD>(sV, V, p.ldv, skp, Sk, tid);
+  cp_async_commit();
+  cp_async_wait<1>();
+  __syncthreads();
+  const bool active = warp * 16 < Sq;
+  const int ngrp = skp >> 4;                                  // 16-key groups (<= 8)
+  // ---- S = Q K^T: 16 rows x skp keys per warp ----
+  float sc[16][4];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) { sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.0f; }
+  if (active) {
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+      uint32_t qa[4];
+      ldsm_x4(qa, sQ + swz_hd<HD>(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kk * 16 + (lane >> 4) * 8));
+#pragma unroll
+      for (int np = 0; np < 8; ++np) {
+        if (np < ngrp) {
+          uint32_t kb[4];
+          ldsm_x4(kb, sK + swz_hd<HD>(np * 16 + (lane & 7) + (lane >> 4) * 8, kk * 16 + ((lane >> 3) & 1) * 8));
+          mma_bf16_16816(sc[2 * np], qa, kb[0], kb[1]);
+          mma_bf16_16816(sc[2 * np + 1], qa, kb[2], kb[3]);
+        }
+      }
+    }
+  }
+  // ---- scale, bias, masks, single-pass softmax (rows r0 = 16w + lane/4 and r1 = r0 + 8) ----
+  const int r0 = warp * 16 + (lane >> 2), r1 = r0 + 8;
+  const int kvl = p.kv_len ? p.kv_len[b] : Sk;
+  const float slope = p.alibi_slopes ? p.alibi_slopes[h] : 0.0f;
+  const int mode0 = (p.qmode && r0 < Sq) ? p.qmode[b * Sq + r0] : 1;
+  const int mode1 = (p.qmode && r1 < Sq) ? p.qmode[b * Sq + r1] : 1;
+  const int jmax0 = p.causal ? (r0 + (Sk - Sq)) : (Sk - 1), jmax1 = p.causal ? (r1 + (Sk - Sq)) : (Sk - 1);
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int n = 0; n < 16; ++n) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = n * 8 + (lane & 3) * 2 + (e & 1);
+      const int mode = (e < 2) ? mode0 : mode1;
+      const int jmax = (e < 2) ? jmax0 : jmax1;
+      float v = sc[n][e] * p.scale + slope * static_cast<float>(j - (Sk - 1));
+      if (j >= Sk) v = -INFINITY;
+      else if (mode == 2) v = 0.0f;
+      else if (j > jmax || j >= kvl) v = -INFINITY;
+      sc[n][e] = v;
+    }
+    mx0 = fmaxf(mx0, fmaxf(sc[n][0], sc[n][1]));
+    mx1 = fmaxf(mx1, fmaxf(sc[n][2], sc[n][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float l0 = 0.0f, l1 = 0.0f;
+  uint32_t pa[8][4];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) {
+    const float p0 = (sc[n][0] == -INFINITY) ? 0.0f : __expf(sc[n][0] - mx0), p1 = (sc[n][1] == -INFINITY) ? 0.0f : __expf(sc[n][1] - mx0);
+    const float p2 = (sc[n][2] == -INFINITY) ? 0.0f : __expf(sc[n][2] - mx1), p3 = (sc[n][3] == -INFINITY) ? 0.0f : __expf(sc[n][3] - mx1);
+    l0 += p0 + p1; l1 += p2 + p3;
+    const int kk = n >> 1;
+    if ((n & 1) == 0) { pa[kk][0] = pack_bf16x2(p0, p1); pa[kk][1] = pack_bf16x2(p2, p3); }
+    else              { pa[kk][2] = pack_bf16x2(p0, p1); pa[kk][3] = pack_bf16x2(p2, p3); }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = (mode0 == 0) ? 0.0f : 1.0f / l0, i1 = (mode1 == 0) ? 0.0f : 1.0f / l1;   // mode 0: attention zeroed (helpers.py:223-229)
+  cp_async_wait<0>();
+  __syncthreads();
+  // ---- O = P V ----
+  float o[HD / 8][4];
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.0f; }
+  if (active) {
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      if (kk < ngrp) {
+#pragma unroll
+        for (int np = 0; np < HD / 16; ++np) {
+          uint32_t vb[4];
+          ldsm_x4_t(vb, sV + swz_hd<HD>(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, np * 16 + (lane >> 4) * 8));
+          mma_bf16_16816(o[2 * np], pa[kk], vb[0], vb[1]);
+          mma_bf16_16816(o[2 * np + 1], pa[kk], vb[2], vb[3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) {
+    const int col = n * 8 + (lane & 3) * 2;
+    if (r0 < Sq) *reinterpret_cast<uint32_t*>(O + static_cast<size_t>(r0) * p.ldo + col) = pack_bf16x2(o[n][0] * i0, o[n][1] * i0);
+    if (r1 < Sq) *reinterpret_cast<uint32_t*>(O + static_cast<size_t>(r1) * p.ldo + col) = pack_bf16x2(o[n][2] * i1, o[n][3] * i1);
+  }
+}
+static inline size_t attn_llm_mma_smem(int Sk, int hd) { return static_cast<size_t>(32 + 2 * ((Sk + 15) & ~15)) * hd * sizeof(bf16); }

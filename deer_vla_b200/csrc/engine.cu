@@ -219,7 +219,20 @@ static int run_attention(int impl, int dtype, const AttnParams& p, std::string* 
     flash_attn_hd64_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const bf16*>(p.Q), p.ldq, reinterpret_cast<const bf16*>(p.K),
                                                  reinterpret_cast<const bf16*>(p.V), p.ldk, reinterpret_cast<bf16*>(p.O), p.ldo, p.Sq, p.Sk,
                                                  p.scale * 1.4426950408889634f);
-  } else if (impl == 2 && attn_small_smem(p.Sq, p.Sk, p.hd) <= 200 * 1024) {
+  } else if ((impl == 2 || impl == 4) && dtype == 0 && p.Sq <= 32 && p.Sk <= 128 && (p.hd == 64 || p.hd == 128) && (p.ldq % 8) == 0 &&
+             (p.ldk % 8) == 0 && (p.ldv % 8) == 0 && (p.ldo % 2) == 0 && ((reinterpret_cast<uintptr_t>(p.Q) | reinterpret_cast<uintptr_t>(p.K) |
+             reinterpret_cast<uintptr_t>(p.V)) & 15) == 0 && (impl == 4 || getenv("DEER_ATTN_LLM_SIMT") == nullptr)) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(attn_llm_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+      cudaFuncSetAttribute(attn_llm_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+      attr_done = true;
+    }
+    dim3 grid(p.H, p.B_host);
+    const size_t sm = attn_llm_mma_smem(p.Sk, p.hd);
+    if (p.hd == 64) attn_llm_mma_kernel<64><<<grid, 64, sm, st>>>(p);
+    else attn_llm_mma_kernel<128><<<grid, 64, sm, st>>>(p);
+  } else if ((impl == 2 || impl == 4) && attn_small_smem(p.Sq, p.Sk, p.hd) <= 200 * 1024) {
     static bool attr_done = false;
     if (!attr_done) {
       cudaFuncSetAttribute(attn_small_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1374,6 +1387,20 @@ extern "C" int deer_op_attention(int impl, int dtype, const void* Q, int ldq, co
   AttnParams a{};
   a.Q = Q; a.K = K; a.V = V; a.O = O; a.ldq = ldq; a.ldk = a.ldv = ldk; a.ldo = ldo; a.Sq = Sq; a.Sk = Sk; a.H = H; a.hd = head_dim;
   a.scale = scale; a.B_host = B;
+  return run_attention(impl, dtype, a, &g_op_err, nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// the same with the LLM-side masks: ALiBi key bias, causal, per-episode valid key count, x-attn media classes, dynamic batch
+extern "C" int deer_op_attention_masked(int impl, int dtype, const void* Q, int ldq, const void* K, const void* V, int ldk, void* O, int ldo,
+                                        int B, int H, int Sq, int Sk, int head_dim, float scale, int causal, const float* alibi_slopes,
+                                        const int32_t* kv_len, const uint8_t* qmode, const int32_t* n_dev, void* stream) {
+  if (!Q || !K || !V || !O) return set_err(nullptr, DEER_E_INVALID, "null pointer");
+  if (impl != 1 && impl != 2 && impl != 4) return set_err(nullptr, DEER_E_INVALID, "masked attention: impl 1 (simt), 2 (auto small) or 4 (mma)");
+  if (impl == 4 && (dtype != 0 || Sq > 32 || Sk > 128 || (head_dim != 64 && head_dim != 128)))
+    return set_err(nullptr, DEER_E_INVALID, "mma LLM attention needs bf16, Sq<=32, Sk<=128, head_dim 64/128");
+  AttnParams a{};
+  a.Q = Q; a.K = K; a.V = V; a.O = O; a.ldq = ldq; a.ldk = a.ldv = ldk; a.ldo = ldo; a.Sq = Sq; a.Sk = Sk; a.H = H; a.hd = head_dim;
+  a.scale = scale; a.B_host = B; a.causal = causal; a.alibi_slopes = alibi_slopes; a.kv_len = kv_len; a.qmode = qmode; a.n_dev = n_dev;
   return run_attention(impl, dtype, a, &g_op_err, nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
 

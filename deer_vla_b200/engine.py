@@ -297,3 +297,26 @@ def op_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float
     if rc != 0:
         raise DeerError(rc, lib.deer_last_error(None).decode())
     return o
+
+
+def op_attention_masked(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, impl: str = "auto", causal: bool = False,
+                        alibi_slopes: Optional[torch.Tensor] = None, kv_len: Optional[torch.Tensor] = None,
+                        qmode: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The LLM-side attentions with their masks through ``deer_op_attention_masked``; shapes as in ``op_attention``.
+    impl "simt" (reference), "mma" (mma.sync kernel) or "auto" (the engine's choice)."""
+    lib = _lib.load()
+    B, Sq, H, hd = q.shape
+    Sk = k.shape[1]
+    dtype = 1 if q.dtype == torch.float32 else 0
+    kv = torch.stack([k, v], dim=2).contiguous()
+    o = torch.zeros_like(q)
+    stream = torch.cuda.current_stream(q.device).cuda_stream
+    kp = kv.data_ptr()
+    vp = kp + H * hd * kv.element_size()
+    opt = [None if t is None else t.contiguous() for t in (alibi_slopes, kv_len, qmode, n_dev)]
+    rc = lib.deer_op_attention_masked({"simt": 1, "auto": 2, "mma": 4}[impl], dtype, _ptr(q), H * hd, C.c_void_p(kp), C.c_void_p(vp),
+                                      2 * H * hd, _ptr(o), H * hd, B, H, Sq, Sk, hd, float(scale), int(causal),
+                                      _ptr(opt[0]), _ptr(opt[1]), _ptr(opt[2]), _ptr(opt[3]), C.c_void_p(stream))
+    if rc != 0:
+        raise DeerError(rc, lib.deer_last_error(None).decode())
+    return o

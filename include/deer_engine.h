@@ -202,6 +202,15 @@ int deer_op_gemm(int impl, int dtype, const void* A, int lda, const void* W, int
 int deer_op_attention(int impl, int dtype, const void* Q, int ldq, const void* K, const void* V, int ldk,
                       void* O, int ldo, int B, int H, int Sq, int Sk, int head_dim, float scale, void* stream);
 
+/* the LLM-side attentions with their masks (gated x-attn: helpers.py:205-229; MPT self-attention: mosaic_gpt_3b.py:158-219):
+ * bias = alibi_slopes[h] * (j - (Sk-1)) (or none), causal (key j visible to query i iff j <= i + Sk - Sq), kv_len[b] valid keys,
+ * qmode[b,i] in {0: zero output, 1: attend, 2: uniform}, n_dev = device-side episode count (<= B) or NULL.  All optional
+ * pointers are DEVICE pointers or NULL.  impl 1 = SIMT reference, 4 = mma.sync kernel (bf16, Sq<=32, Sk<=128, head_dim 64/128),
+ * 2 = what the engine picks. */
+int deer_op_attention_masked(int impl, int dtype, const void* Q, int ldq, const void* K, const void* V, int ldk, void* O, int ldo,
+                             int B, int H, int Sq, int Sk, int head_dim, float scale, int causal, const float* alibi_slopes,
+                             const int32_t* kv_len, const uint8_t* qmode, const int32_t* n_dev, void* stream);
+
 /* bring-up / regression probe of the tensor-core attention's second GEMM: O[128,64] = P[128,K] @ V[K,64] with P staged in
  * tensor memory (tcgen05.st) as the A operand and V read in its natural [key][d] layout as an MN-major B operand. */
 int deer_op_pv_probe(const void* P, const void* V, float* O, int K, int lbo_bytes, int sbo_bytes, int kstep_bytes, void* stream);

@@ -133,3 +133,59 @@ def test_pv_probe_tmem_a_operand_and_mn_major_b():
         assert lib.deer_op_pv_probe(C.c_void_p(P.data_ptr()), C.c_void_p(V.data_ptr()), C.c_void_p(O.data_ptr()), K, 1024, 1024, 2048, None) == 0
         torch.cuda.synchronize()
         assert (O - P.float() @ V.float()).abs().max().item() <= 1e-3 * K ** 0.5
+
+
+def _masked_ref(q, k, v, scale, causal, slopes, kv_len, qmode):
+    """fp32 torch reference with the kernels' semantics (masked keys excluded; mode 0 -> zeros; mode 2 -> uniform over all keys)."""
+    B, Sq, H, hd = q.shape
+    Sk = k.shape[1]
+    s = torch.einsum("bihd,bjhd->bhij", q.float(), k.float()) * scale
+    j = torch.arange(Sk, device=q.device)
+    i = torch.arange(Sq, device=q.device)
+    if slopes is not None:
+        s = s + slopes.view(1, H, 1, 1) * (j - (Sk - 1)).view(1, 1, 1, Sk).float()
+    dead = torch.zeros(B, 1, Sq, Sk, dtype=torch.bool, device=q.device)
+    if causal:
+        dead |= (j.view(1, Sk) > (i.view(Sq, 1) + (Sk - Sq))).view(1, 1, Sq, Sk)
+    if kv_len is not None:
+        dead |= (j.view(1, 1, 1, Sk) >= kv_len.view(B, 1, 1, 1))
+    s = s.masked_fill(dead, float("-inf"))
+    if qmode is not None:
+        s = torch.where((qmode == 2).view(B, 1, Sq, 1), torch.zeros_like(s), s)
+    p = torch.softmax(s, dim=-1)
+    o = torch.einsum("bhij,bjhd->bihd", p, v.float())
+    if qmode is not None:
+        o = o * (qmode != 0).view(B, Sq, 1, 1).float()
+    return o
+
+
+@pytest.mark.parametrize("case", [
+    dict(B=5, H=16, Sq=32, Sk=32, hd=128, causal=True, alibi=True, ragged=True, modes=False),     # MPT-1B self-attention
+    dict(B=3, H=32, Sq=32, Sk=32, hd=128, causal=True, alibi=True, ragged=False, modes=False),    # MPT-7B self-attention
+    dict(B=4, H=8, Sq=32, Sk=128, hd=64, causal=False, alibi=False, ragged=False, modes=True),    # gated x-attn, media classes
+    dict(B=2, H=2, Sq=13, Sk=13, hd=128, causal=True, alibi=True, ragged=True, modes=False),      # short instruction
+    dict(B=3, H=3, Sq=7, Sk=100, hd=64, causal=False, alibi=False, ragged=False, modes=True),     # ragged key count
+    dict(B=2, H=4, Sq=17, Sk=128, hd=64, causal=False, alibi=False, ragged=False, modes=False),
+    dict(B=6, H=2, Sq=32, Sk=32, hd=64, causal=True, alibi=True, ragged=True, modes=False),
+])
+def test_llm_attention_mma_vs_simt_and_torch(case):
+    from deer_vla_b200.engine import op_attention_masked
+    B, H, Sq, Sk, hd = case["B"], case["H"], case["Sq"], case["Sk"], case["hd"]
+    g = torch.Generator(device="cuda").manual_seed(B * 131 + Sq)
+    q = torch.randn(B, Sq, H, hd, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B, Sk, H, hd, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Sk, H, hd, device="cuda", generator=g).bfloat16()
+    scale = hd ** -0.5
+    slopes = (0.5 ** torch.arange(1, H + 1, device="cuda").float() * 4.0 / H).contiguous() if case["alibi"] else None
+    kv_len = torch.randint(max(1, Sk // 2), Sk + 1, (B,), device="cuda", generator=g, dtype=torch.int32) if case["ragged"] else None
+    qmode = torch.randint(0, 3, (B, Sq), device="cuda", generator=g, dtype=torch.int32).to(torch.uint8) if case["modes"] else None
+    n_dev = torch.tensor([B - 1], device="cuda", dtype=torch.int32)                      # last episode inactive: its rows stay untouched
+    ref = _masked_ref(q, k, v, scale, case["causal"], slopes, kv_len, qmode)
+    outs = {}
+    for impl in ("simt", "mma", "auto"):
+        outs[impl] = op_attention_masked(q, k, v, scale, impl=impl, causal=case["causal"], alibi_slopes=slopes, kv_len=kv_len,
+                                         qmode=qmode, n_dev=n_dev).float()
+        assert torch.all(outs[impl][B - 1] == 0), impl                                     # dynamic batch honoured
+        err = (outs[impl][: B - 1] - ref[: B - 1]).abs().max().item()
+        assert err <= 2e-2, (impl, err)                                                    # bf16 output rounding of O(1) values
+    assert (outs["mma"] - outs["simt"]).abs().max().item() <= 2e-2
