@@ -61,6 +61,7 @@ SYMBOLS = {
     "deer_reset": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_int]),
     "deer_step": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_uint32, _P, _P, _P, _P, _P, _P]),
     "deer_step_host": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_uint32, _P, _P, _P, _P, _P]),
+    "deer_step_generate": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P]),
     "deer_preprocess_u8": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "deer_step_host_u8": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_uint32,
                                     _P, _P, _P, _P, _P]),

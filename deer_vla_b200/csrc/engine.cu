@@ -332,6 +332,8 @@ struct deer_ctx {
   struct AxisTab { int* bounds = nullptr; int* kk = nullptr; int ksize = 0; int need = 0; };
   std::map<std::pair<int, int>, AxisTab> axis_tabs;
   uint8_t* u8_stage[2] = {nullptr, nullptr}; size_t u8_cap[2] = {0, 0};
+  // generate (calibration) mode
+  const int32_t* gen_commit_layer = nullptr; float *pend_h = nullptr, *pend_c = nullptr; uint8_t* pend_flag = nullptr;
   GemmCtx gemm;
   LaunchStats stats;
   int64_t steps = 0;
@@ -1050,7 +1052,9 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
                      int32_t* exit_out, float* delta_out, cudaStream_t st) {
   const deer_config& f = c->cfg;
   StepImpl<T> s{c, st, n, S, 0};
-  const bool full_depth = (flags & DEER_FLAG_FULL_DEPTH) != 0;
+  const bool gen = (flags & DEER_FLAG_GENERATE) != 0;
+  const bool full_depth = gen || (flags & DEER_FLAG_FULL_DEPTH) != 0;
+  const int nthr_step = gen ? (int)c->exits.size() : c->n_thr;           // generate mode reports a delta for EVERY exit
   if (!pose_out) pose_out = c->o_pose;
   if (!grip_out) grip_out = c->o_grip;
   if (!action_out) action_out = c->o_action;
@@ -1058,8 +1062,9 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
   if (!delta_out) delta_out = c->o_delta;
   c->tap_n = n; c->tap_S = S;
   init_episodes_kernel<<<(n + 127) / 128, 128, 0, s.st>>>(c->meta[0], c->n_active, slots, ids, mask, timesteps, n, S, f.media_token_id,
-                                                          f.steps_per_stage, c->n_thr, exit_out, delta_out);
+                                                          f.steps_per_stage, nthr_step, exit_out, delta_out);
   KLAUNCH_CHECK("init_episodes");
+  if (gen) CK(cudaMemsetAsync(c->pend_flag, 0, n, s.st));
   c->n_probes_last = 0; c->n_last = n;
   c->gemm.epoch = 0;
   if (c->gemm.profile) {
@@ -1074,8 +1079,9 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
   if (c->dtype == 1) embed_kernel<float><<<n * S, 256, 0, s.st>>>(ids, reinterpret_cast<const float*>(c->wte), c->x[0], n * S, f.d_model, f.vocab);
   else embed_kernel<bf16><<<n * S, 256, 0, s.st>>>(ids, reinterpret_cast<const bf16*>(c->wte), c->x[0], n * S, f.d_model, f.vocab);
   KLAUNCH_CHECK("embed");
-  const int last_layer = (static_exit >= 0) ? static_exit : c->ctrl_max_layer;
+  const int last_layer = (static_exit >= 0) ? static_exit : (gen ? c->exits.back() : c->ctrl_max_layer);
   const int first_exit = c->exits[0];
+  const int first_prev = gen ? 0 : first_exit - 1;        // generate mode compares the first exit with layer 0 (value_net.py:136)
   for (int li = 0; li <= last_layer; ++li) {
     RET(s.llm_layer(li));
     bool is_exit = false;
@@ -1085,7 +1091,7 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
     } else {
       for (size_t k = 0; k < c->exits.size(); ++k)
         if (c->exits[k] == li) { is_exit = true; exit_idx = (int)k; }
-      if (li == first_exit - 1) {
+      if (li == first_prev) {
         // first exit compares with the head applied to the PREVIOUS layer's features (value_net.py:122-125)
         RET(s.head_eval());
         copy_pose_kernel<<<(n * 6 + 127) / 128, 128, 0, s.st>>>(c->cur_pose, c->meta[s.cur].prev_pose, n, s.nact());
@@ -1095,10 +1101,11 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
     if (!is_exit) continue;
     RET(s.head_eval());
     GateParams g{};
-    g.layer = li; g.exit_idx = (exit_idx >= 0 && exit_idx < c->n_thr) ? exit_idx : -1;
-    g.forced = (static_exit >= 0) ? 1 : (li >= c->ctrl_max_layer ? 1 : 0);
+    g.layer = li; g.exit_idx = (exit_idx >= 0 && exit_idx < nthr_step) ? exit_idx : -1;
+    g.forced = (static_exit >= 0) ? 1 : (li >= last_layer ? 1 : 0);
+    if (gen) { g.commit_layer = c->gen_commit_layer; g.pend_flag = c->pend_flag; }
     g.full_depth = full_depth ? 1 : 0; g.has_prev = (static_exit >= 0) ? 0 : 1;
-    g.threshold_type = f.threshold_type; g.n_thr = c->n_thr; g.thresholds = c->thr_dev;
+    g.threshold_type = f.threshold_type; g.n_thr = nthr_step; g.thresholds = c->thr_dev;
     g.cur_pose = c->cur_pose; g.cur_grip = c->cur_grip; g.cur_exit_id = c->cur_exit_id;
     g.pose_out = pose_out; g.grip_out = grip_out; g.action_out = action_out; g.exit_out = exit_out; g.delta_out = delta_out;
     g.exit_flag = c->exit_flag; g.src_of_new = c->src_of_new;
@@ -1116,6 +1123,18 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
     KLAUNCH_CHECK("exit_gate");
     c->n_probes_last++;
     c->gemm.epoch = c->n_probes_last;
+    if (gen) {
+      park_state_kernel<<<dim3(n, f.lstm_layers), 256, 0, s.st>>>(c->exit_flag, c->meta[s.cur].orig, c->cand_h, c->cand_c, c->pend_h, c->pend_c,
+                                                               f.lstm_layers, f.lstm_hidden, f.max_batch, n);
+      KLAUNCH_CHECK("park_state");
+      if (g.forced) {
+        commit_pending_kernel<<<dim3(n, f.lstm_layers), 256, 0, s.st>>>(c->pend_flag, slots, c->pend_h, c->pend_c, c->h_state, c->c_state,
+                                                                     f.lstm_layers, f.lstm_hidden, n);
+        KLAUNCH_CHECK("commit_pending");
+        break;
+      }
+      continue;                               // nobody leaves before the last layer: no compaction
+    }
     commit_state_kernel<<<dim3(n, f.lstm_layers), 256, 0, s.st>>>(c->exit_flag, c->meta[s.cur].slot, c->cand_h, c->cand_c, c->h_state, c->c_state,
                                                                f.lstm_layers, f.lstm_hidden, f.max_batch, n, c->n_active + s.cur);
     KLAUNCH_CHECK("commit_state");
@@ -1248,6 +1267,31 @@ extern "C" int deer_step(deer_ctx* c, int n, const int32_t* slots, const float* 
     r = step_graph(c, n, slots, rgb, gripper, ids, mask, S, timesteps, static_exit, flags, pose_out, gripper_out, action_out, exit_out, delta_out, st);
   else
     r = step_dispatch(c, n, slots, rgb, gripper, ids, mask, S, timesteps, static_exit, flags, pose_out, gripper_out, action_out, exit_out, delta_out, st);
+  mark_done(c, st);
+  if (r == DEER_OK) c->steps++;
+  return r;
+}
+
+extern "C" int deer_step_generate(deer_ctx* c, int n, const int32_t* slots, const float* rgb, const float* gripper, const int64_t* ids,
+                                  const uint8_t* mask, int S, const int32_t* commit_layer, float* delta_out, void* stream) {
+  if (!c) return set_err(nullptr, DEER_E_INVALID, "null ctx");
+  if (!slots || !rgb || !gripper || !ids || !mask || !commit_layer || !delta_out) return set_err(&c->err, DEER_E_INVALID, "null pointer");
+  RET(validate_step(c, n, S, -1, DEER_FLAG_FULL_DEPTH));
+  if (c->exits[0] == 0) return set_err(&c->err, DEER_E_INVALID, "generate mode needs 0 not in exit_list (value_net.py:135)");
+  cudaSetDevice(c->device);
+  if (!c->pend_h) {
+    const size_t per = (size_t)c->cfg.max_batch * c->cfg.lstm_layers * c->cfg.lstm_hidden * 4;
+    RET(dalloc(c, reinterpret_cast<void**>(&c->pend_h), per, false));
+    RET(dalloc(c, reinterpret_cast<void**>(&c->pend_c), per, false));
+    RET(dalloc(c, reinterpret_cast<void**>(&c->pend_flag), c->cfg.max_batch, false));
+  }
+  c->stats.step = 0; c->stats.gemm_step = 0; c->stats.gemm_flops_step = 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  order_after_last(c, st);
+  c->gen_commit_layer = commit_layer;
+  int r = step_dispatch(c, n, slots, rgb, gripper, ids, mask, S, nullptr, -1, DEER_FLAG_FULL_DEPTH | DEER_FLAG_GENERATE, nullptr, nullptr,
+                        nullptr, nullptr, delta_out, st);
+  c->gen_commit_layer = nullptr;
   mark_done(c, st);
   if (r == DEER_OK) c->steps++;
   return r;

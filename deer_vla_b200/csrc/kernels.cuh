@@ -376,6 +376,8 @@ struct GateParams {
   const float* cur_pose;     // [r,6]
   const float* cur_grip;     // [r]
   int* cur_exit_id;          // [slots] value_net.py:294
+  const int* commit_layer;   // generate mode: [orig] exit layer whose candidate LSTM state becomes the carried one (or nullptr)
+  uint8_t* pend_flag;        // generate mode: [orig] set when that candidate has been captured
   // outputs indexed by orig
   float* pose_out; float* grip_out; float* action_out; int* exit_out; float* delta_out;
   // compaction
@@ -437,7 +439,13 @@ exit_gate_kernel(GateParams g, EpisodeMeta m, const int* __restrict__ n_cur, int
       }
       if (g.exit_out) g.exit_out[o] = g.layer;
     }
-    g.exit_flag[r] = ex ? 1 : 0;
+    if (g.commit_layer) {                                           // flamingo_mpt.py:484-492: a drawn exit's features feed the history
+      const int hit = (g.commit_layer[o] == g.layer) ? 1 : 0;
+      g.exit_flag[r] = hit;
+      if (hit) g.pend_flag[o] = 1;
+    } else {
+      g.exit_flag[r] = ex ? 1 : 0;
+    }
     survive = ex ? 0 : 1;
   }
   // exclusive scan of `survive` over the CTA
@@ -484,6 +492,27 @@ __global__ void commit_state_kernel(const uint8_t* __restrict__ exit_flag, const
     h_state[dst + j] = cand_h[src + j];
     c_state[dst + j] = cand_c[src + j];
   }
+}
+
+// generate mode: candidates captured at the drawn exit are parked per row (state layout) and committed after the last probe,
+// so that every probe of the frame starts from the same carried state
+__global__ void park_state_kernel(const uint8_t* __restrict__ exit_flag, const int* __restrict__ orig, const float* __restrict__ cand_h,
+                                  const float* __restrict__ cand_c, float* __restrict__ pend_h, float* __restrict__ pend_c,
+                                  int layers, int Hh, int nstride, int n) {
+  const int r = blockIdx.x, l = blockIdx.y;
+  if (r >= n || !exit_flag[r]) return;
+  const size_t src = (static_cast<size_t>(l) * nstride + r) * Hh;
+  const size_t dst = (static_cast<size_t>(orig[r]) * layers + l) * Hh;
+  for (int j = threadIdx.x; j < Hh; j += blockDim.x) { pend_h[dst + j] = cand_h[src + j]; pend_c[dst + j] = cand_c[src + j]; }
+}
+__global__ void commit_pending_kernel(const uint8_t* __restrict__ pend_flag, const int* __restrict__ slots, const float* __restrict__ pend_h,
+                                      const float* __restrict__ pend_c, float* __restrict__ h_state, float* __restrict__ c_state,
+                                      int layers, int Hh, int n) {
+  const int o = blockIdx.x, l = blockIdx.y;
+  if (o >= n || !pend_flag[o]) return;
+  const size_t src = (static_cast<size_t>(o) * layers + l) * Hh;
+  const size_t dst = (static_cast<size_t>(slots[o]) * layers + l) * Hh;
+  for (int j = threadIdx.x; j < Hh; j += blockDim.x) { h_state[dst + j] = pend_h[src + j]; c_state[dst + j] = pend_c[src + j]; }
 }
 
 // gather survivors into the other half of the ping-pong buffers

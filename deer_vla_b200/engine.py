@@ -199,6 +199,30 @@ class DeerEngine:
                                             _ptr(out["exit_layer"]), _ptr(out["delta"])))
         return out
 
+    def step_generate(self, rgb: torch.Tensor, gripper: torch.Tensor, ids: torch.Tensor, commit_layer: torch.Tensor,
+                      mask: Optional[torch.Tensor] = None, slots: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One frame of the calibration pass in the training layout (``deer_step_generate``): CUDA tensors in, returns the
+        delta columns of this frame, (n, len(exit_list)), on the device.  ``commit_layer`` (n,) int: the exit layer whose
+        candidate LSTM state is carried to the next frame (flamingo_mpt.py:484-492)."""
+        n, S = int(ids.shape[0]), int(ids.shape[1])
+        dev = self.device
+        assert rgb.is_cuda and gripper.is_cuda
+        if mask is None:
+            mask = torch.ones(n, S, dtype=torch.uint8, device=dev)
+        if slots is None:
+            slots = torch.arange(n, dtype=torch.int32, device=dev)
+        rgb = rgb.reshape(n, 3, self.cfg.image_size, self.cfg.image_size).to(torch.float32).contiguous()
+        gripper = gripper.reshape(n, 3, self.cfg.image_size, self.cfg.image_size).to(torch.float32).contiguous()
+        ids = ids.to(dev, torch.int64).contiguous()
+        mask = mask.to(dev, torch.uint8).contiguous()
+        slots = slots.to(dev, torch.int32).contiguous()
+        commit_layer = commit_layer.to(dev, torch.int32).contiguous()
+        delta = torch.empty(n, len(self.exit_list), dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self.lib.deer_step_generate(self._h, n, _ptr(slots), _ptr(rgb), _ptr(gripper), _ptr(ids), _ptr(mask), S,
+                                                _ptr(commit_layer), _ptr(delta), C.c_void_p(stream)))
+        return delta
+
     def preprocess(self, frames_u8: torch.Tensor) -> torch.Tensor:
         """On-device open_clip image transform: CUDA uint8 [n,H,W,3] -> fp32 [n,3,S,S] (bit-exact Pillow bicubic + normalise)."""
         assert frames_u8.is_cuda and frames_u8.dtype == torch.uint8 and frames_u8.ndim == 4 and frames_u8.shape[-1] == 3

@@ -129,3 +129,33 @@ def generate_action_values(engine, batches) -> torch.Tensor:
         out = engine.step(full_depth=True, **b)
         cols.append(out["delta"].detach().float().cpu().t())
     return torch.cat(cols, dim=1)
+
+
+@torch.no_grad()
+def generate_action_values_window(engine, windows, window_size: int = 12, layer_indices=None, generator=None) -> torch.Tensor:
+    """``generate_action_values`` in the reference's own layout (value_net.py:300-399): ``windows`` yields dicts with
+    ``rgb``/``gripper`` (bs, window, 3, H, W) CUDA tensors and ``ids`` (bs, S) [``mask`` (bs, S)] -- what the CALVIN loader
+    hands over (value_net.py:331-346).  Per window the exit layer whose features stand in for each past frame is drawn
+    uniformly from the exit list (flamingo_mpt.py:486-487) unless ``layer_indices`` supplies an iterable of (bs, window)
+    tensors.  Returns the (n_exit, n_windows * window_size//2) delta table ``ExitController.set_threshold(values=...)`` takes
+    (value_net.py:134-160: seq_id = window//2-1 .. window-2, bs-major order)."""
+    exits = torch.tensor(engine.exit_list, dtype=torch.int64)
+    li_iter = iter(layer_indices) if layer_indices is not None else None
+    cols = []
+    for w in windows:
+        rgb, grip, ids = w["rgb"], w["gripper"], w["ids"]
+        bs = rgb.shape[0]
+        assert rgb.shape[1] == window_size and bs <= engine.max_batch
+        if li_iter is not None:
+            li = next(li_iter).to(torch.int64).cpu()
+        else:
+            li = exits[torch.randint(0, len(exits), (bs, window_size), generator=generator)]
+        engine.reset(range(bs))
+        per_t = []
+        for t in range(window_size - 1):
+            d = engine.step_generate(rgb[:, t], grip[:, t], ids, li[:, t], mask=w.get("mask"))
+            if t >= window_size // 2 - 1:
+                per_t.append(d)
+        # (T/2, bs, n_exit) -> (n_exit, bs, T/2) -> (n_exit, bs*T/2)
+        cols.append(torch.stack(per_t).permute(2, 1, 0).reshape(len(exits), -1).float().cpu())
+    return torch.cat(cols, dim=1)

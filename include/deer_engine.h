@@ -43,6 +43,8 @@ enum { DEER_THR_L2 = 0, DEER_THR_MEAN = 1, DEER_THR_MAX = 2, DEER_THR_COSINE = 3
 #define DEER_FLAG_FULL_DEPTH 1u  /* calibration: ignore thresholds, run to the last enabled exit,
                                     record delta at every exit (value_net.py:300-399 "generate" use) */
 
+#define DEER_FLAG_GENERATE 2u    /* internal to deer_step_generate (implies FULL_DEPTH) */
+
 typedef struct deer_ctx deer_ctx;
 
 /* Model + exit configuration.  Mirrors what eval_calvin.py derives from its flags and the
@@ -169,6 +171,17 @@ typedef struct deer_profile {
 } deer_profile;
 int deer_set_profile(deer_ctx* ctx, int enable);
 int deer_get_profile(deer_ctx* ctx, deer_profile* out);
+
+/* One frame of the threshold-calibration pass in the reference's TRAINING layout -- replaces generate_action_values
+ * (value_net.py:300-399): MPTFlamingo.forward(return_in_feat, only_extra_exit) over windows of frames (flamingo_mpt.py:476-492)
+ * followed by ActionValueNet.forward(mode='generate') (value_net.py:134-160).  Call it for frames t = 0 .. window-2 of n
+ * windows (slots reset before t = 0).  Every layer runs; the head probes layer 0 and every exit of the exit list from the
+ * carried LSTM state; delta_out[i, k] = delta between ([0]+exit_list)[k] and [k+1] (DEVICE, [n, deer_num_exits()]); the
+ * state carried to the next frame is the candidate computed at exit layer commit_layer[i] (DEVICE int32 [n]; the reference
+ * draws it uniformly from the exit list per window and frame).  Deltas of frames window/2-1 .. window-2 form the table the
+ * threshold solver consumes.  All pointers are DEVICE pointers. */
+int deer_step_generate(deer_ctx* ctx, int n, const int32_t* slots, const float* rgb, const float* gripper, const int64_t* ids,
+                       const uint8_t* mask, int S, const int32_t* commit_layer, float* delta_out, void* stream);
 
 /* on-device image transform -- replaces preprocess_image -> open_clip image_transform for raw uint8 camera frames
  * (data.py:898-902; eval_utils.py:292-296,317-321): torchvision Resize(image_size, BICUBIC) on a PIL image (bit-exact

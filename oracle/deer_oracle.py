@@ -607,6 +607,59 @@ def solve_thresholds(values: Tensor, exit_ratio: float, exit_dist: str = "exp",
 
 
 # --------------------------------------------------------------------------------------
+# threshold calibration in the training layout ("generate" mode)
+# --------------------------------------------------------------------------------------
+@torch.no_grad()
+def window_hidden_states(cfg: DeerConfig, W: Dict[str, Tensor], rgb: Tensor, gripper: Tensor, ids: Tensor,
+                         mask: Optional[Tensor] = None) -> List[Tensor]:
+    """``MPTFlamingo.forward`` in the training layout (flamingo_mpt.py:308-461 without an exit controller): every frame
+    of every window runs all ``n_layers`` layers.  rgb/gripper (bs, win, 3, H, W); ids (bs, S) repeated over the window
+    (value_net.py:337-346).  Returns the post-block hidden states, a list of n_layers tensors (bs*win, S, d)."""
+    bs, win = rgb.shape[:2]
+    S = ids.shape[1]
+    ids_f = ids.unsqueeze(1).repeat(1, win, 1).flatten(0, 1)
+    mask_f = torch.ones_like(ids_f) if mask is None else mask.unsqueeze(1).repeat(1, win, 1).flatten(0, 1)
+    media, _ = encode_vision(cfg, W, rgb.flatten(0, 1), gripper.flatten(0, 1))
+    media_locations = ids_f == cfg.media_token_id
+    x = W["lang_encoder.transformer.wte.weight"][ids_f]
+    attn_bias = mpt_attn_bias(cfg, mask_f)
+    hidden = []
+    for l in range(cfg.n_layers):
+        x = flamingo_layer_forward(cfg, W, l, x, media, media_locations, attn_bias)
+        hidden.append(x)
+    return hidden
+
+
+@torch.no_grad()
+def generate_deltas(cfg: DeerConfig, W: Dict[str, Tensor], hidden: List[Tensor], layer_idx: Tensor, window: int = 12) -> Tensor:
+    """``ActionValueNet.forward(mode='generate')`` (value_net.py:134-160) on top of the random-layer features of
+    flamingo_mpt.py:484-492.  ``layer_idx`` (bs, window): the exit layer whose features stand in for each PAST frame
+    (the reference draws it with torch.randint over get_all_exit_idx()).  For seq_id in window//2-1 .. window-2 and every
+    exit i in [0]+exit_list the head runs as a fresh LSTM over [rand feats of frames < seq_id] + [layer-i feats of frame
+    seq_id] (window path of DeterministicDecoder.forward, action_head.py:596-602, last_action) and delta is taken between
+    consecutive exits.  Returns (n_exit, bs * window//2) in the reference's (bs-major, seq-minor) order."""
+    S, d = hidden[0].shape[1:]
+    feats = [h.reshape(-1, window, S, d) for h in hidden]                     # (bs, win, S, d) per layer
+    bs = feats[0].shape[0]
+    all_f = torch.stack(feats, dim=2)                                          # (bs, win, n_layers, S, d)
+    gi = layer_idx.reshape(bs, window, 1, 1, 1).expand(-1, -1, 1, S, d)
+    rand_feat = torch.gather(all_f, 2, gi).squeeze(2)                          # (bs, win, S, d)  flamingo_mpt.py:489-490
+    exits = [0] + list(cfg.exit_list)
+    per_seq = []
+    for seq_id in range(window // 2 - 1, window - 1):
+        acts = []
+        for i in exits:
+            seq = torch.cat([rand_feat[:, :seq_id], feats[i][:, seq_id:seq_id + 1]], dim=1)      # (bs, seq_id+1, S, d)
+            state = None
+            for t in range(seq_id + 1):                                        # nn.LSTM over the sequence from a zero state
+                pose, _, _, state = head_forward(cfg, W, seq[:, t], state)
+            acts.append(pose)                                                  # last_action: the last frame's output
+        per_seq.append(torch.stack(acts))                                      # (n_exit+1, bs, 6)
+    a = torch.stack(per_seq).permute(1, 2, 0, 3)                               # (n_exit+1, bs, win/2, 6)
+    return get_delta(a[:-1], a[1:], cfg.threshold_type).flatten(1, 2)
+
+
+# --------------------------------------------------------------------------------------
 # the per-timestep forward with dynamic exit
 # --------------------------------------------------------------------------------------
 @dataclass

@@ -354,6 +354,39 @@ def golden_full(S=32):
     np.savez_compressed(os.path.join(GOLD, "full3b.npz"), **out)
 
 
+def golden_generate(bs=2, win=12, S=16):
+    """Calibration pass in the training layout: the unmodified reference (MPTFlamingo.forward with return_in_feat /
+    only_extra_exit as value_net.py:370-381 calls it, then ActionValueNet.forward(mode='generate')) vs the oracle's
+    restatement, tiny config -> generate_tiny.npz (random layer indices as drawn by the reference, delta table)."""
+    cfg = O.config_tiny()
+    W = O.synth_weights(cfg, 0)
+    model, ctrl, _ = ref_shims.build_reference_model(cfg, W, [1e8] * cfg.n_thresholds)
+    model.window_size = win
+    model.set_all_exit_window_size(win)
+    ctrl.value_net.window_size = win
+    eps = list(range(40, 40 + bs))
+    rgb = torch.stack([torch.stack([O.synth_image(cfg, e, t, 0) for t in range(win)]) for e in eps])
+    grip = torch.stack([torch.stack([O.synth_image(cfg, e, t, 1) for t in range(win)]) for e in eps])
+    ids = torch.stack([O.synth_tokens(cfg, e, S) for e in eps])
+    images = rgb.unsqueeze(2).unsqueeze(2).flatten(0, 1)
+    gripper = grip.unsqueeze(2).unsqueeze(2).flatten(0, 1)
+    input_ids = ids.unsqueeze(1).repeat(1, win, 1).flatten(0, 1)
+    torch.manual_seed(123)
+    with torch.no_grad():
+        final_output, _, _, rand_layer_feat, rand_idx = model(
+            vision_x=images, lang_x=input_ids, attention_mask=torch.ones_like(input_ids), vision_gripper=gripper,
+            state_tensor=None, with_gripper_logits=True, return_in_feat=True, only_extra_exit=True)
+        sim = ctrl.value_net(final_output.hidden_states, mode="generate", rand_layer_feat=rand_layer_feat)
+    hidden = O.window_hidden_states(cfg, W, rgb, grip, ids)
+    mine = O.generate_deltas(cfg, W, hidden, rand_idx, win)
+    hd = max(float((a - b).abs().max()) for a, b in zip(final_output.hidden_states, hidden))
+    dd = float((sim - mine).abs().max())
+    print(f"[generate] reference vs oracle: hidden {hd:.2e}, delta table {tuple(sim.shape)} {dd:.2e}; layer idx {rand_idx.tolist()}")
+    assert hd < 5e-5 and dd < 5e-6
+    np.savez_compressed(os.path.join(GOLD, "generate_tiny.npz"), layer_idx=rand_idx.numpy().astype(np.int32), deltas=sim.numpy(),
+                        episodes=np.array(eps), window=win, S=S)
+
+
 def golden_yardstick(S=32, T=2):
     """Rounding yardstick at OpenFlamingo-3B size: the oracle in fp32 and with bf16-rounded
     contraction operands on the same inputs, full depth (every exit probed), 2 episodes x T steps -> yardstick3b.npz."""
@@ -386,14 +419,19 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--yardstick-only", action="store_true")
+    ap.add_argument("--generate-only", action="store_true")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     if a.yardstick_only:
         golden_yardstick()
         sys.exit(0)
+    if a.generate_only:
+        golden_generate()
+        sys.exit(0)
     golden_thresholds()
     xcheck_third_party()
     golden_tiny()
+    golden_generate()
     if a.full:
         golden_full()
         golden_yardstick()

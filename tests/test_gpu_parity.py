@@ -360,3 +360,39 @@ def test_full3b_batch_invariance(full3b, gold_full):
         assert int(one["exit_layer"][0]) == int(big["exit_layer"][i])
         assert torch.equal(one["pose"][0].cpu(), big["pose"][i]), i
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# threshold calibration in the training layout
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("bf16", 1.5e-2)])
+def test_generate_mode_vs_reference_golden(prec, tol):
+    """deer_step_generate over 11 frames of 2 windows == the unmodified reference's generate_action_values table
+    (golden made by oracle/make_golden.py::golden_generate with the layer indices the reference drew)."""
+    from deer_vla_b200.value_net import generate_action_values_window
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "generate_tiny.npz"))
+    ocfg = O.config_tiny()
+    W = O.synth_weights(ocfg, 0)
+    win, S = int(g["window"]), int(g["S"])
+    eps = [int(e) for e in g["episodes"]]
+    eng = _engine(ocfg, W, max_batch=len(eps), max_seq=S, precision=prec)
+    rgb = torch.stack([torch.stack([O.synth_image(ocfg, e, t, 0) for t in range(win)]) for e in eps]).cuda()
+    grip = torch.stack([torch.stack([O.synth_image(ocfg, e, t, 1) for t in range(win)]) for e in eps]).cuda()
+    ids = torch.stack([O.synth_tokens(ocfg, e, S) for e in eps]).cuda()
+    li = torch.from_numpy(g["layer_idx"]).long()
+    table = generate_action_values_window(eng, [{"rgb": rgb, "gripper": grip, "ids": ids}], window_size=win, layer_indices=[li])
+    want = torch.from_numpy(g["deltas"])
+    assert table.shape == want.shape
+    err = float((table - want).abs().max())
+    print(f"\n[generate {prec}] max |delta - reference| = {err:.3e} (table max {float(want.max()):.3e})")
+    assert err <= tol, err
+    # the dynamic-exit path is untouched by a calibration pass: same thresholds -> same step as a fresh engine
+    eng.set_thresholds([float(x) for x in want.mean(1)[: ocfg.n_thresholds - 1]] + [1e8])
+    eng.reset()
+    a = eng.step(rgb[:, 0], grip[:, 0], ids)
+    eng2 = _engine(ocfg, W, max_batch=len(eps), max_seq=S, precision=prec)
+    eng2.set_thresholds(eng.thresholds)
+    eng2.reset()
+    b = eng2.step(rgb[:, 0], grip[:, 0], ids)
+    assert torch.equal(a["exit_layer"], b["exit_layer"]) and torch.equal(a["action"], b["action"])
+    eng.close(); eng2.close()
