@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import os
 import re
-from typing import Any, Dict, Mapping, Optional
+from typing import Any, Dict, List, Mapping, Optional, Tuple
 
 from .config import DeerConfig, config_3b, config_9b
 
@@ -98,3 +98,69 @@ def config_from_checkpoint(ckpt: Mapping[str, Any], path: str = "", max_layer: O
 def state_dict_of(ckpt: Mapping[str, Any]) -> Mapping[str, Any]:
     """``model_state_dict`` if present (DeeR .pth), else the mapping itself (OpenFlamingo .pt / plain state dict)."""
     return ckpt.get("model_state_dict", ckpt)
+
+
+# ---------------------------------------------------------------------------------------------------
+# assembling the model's state dict from its published pieces
+# ---------------------------------------------------------------------------------------------------
+_XATTN_ALIAS = re.compile(r"^lang_encoder\.gated_cross_attn_layers\.(\d+)\.(.+)$")
+_HF_BLOCK = re.compile(r"^transformer\.blocks\.(\d+)\.(.+)$")
+
+
+def _strip_module(k: str) -> str:
+    return k[len("module."):] if k.startswith("module.") else k
+
+
+def assemble_state_dict(cfg: DeerConfig, hf_lm: Optional[Mapping[str, Any]] = None, clip: Optional[Mapping[str, Any]] = None,
+                        open_flamingo: Optional[Mapping[str, Any]] = None, deer: Optional[Mapping[str, Any]] = None,
+                        ) -> Tuple[Dict[str, Any], List[str]]:
+    """Merge the pieces a DeeR model is built from, in the reference's load order, into ONE dict keyed like
+    ``MPTFlamingo.state_dict()`` (what ``DeerEngine.load_state_dict`` / ``deer_load_weight`` consume):
+
+    1. ``clip``: an open_clip checkpoint / ``state_dict()`` -- ``visual.*`` becomes ``vision_encoder.*`` (factory.py:109-114;
+       MPTFlamingo keeps only ``vision_encoder.visual``), the text tower is dropped;
+    2. ``hf_lm``: the HF MPT causal-LM state dict -- ``transformer.blocks.i.*`` becomes
+       ``lang_encoder.transformer.blocks.i.decoder_layer.*`` (FlamingoLayer wrapping, flamingo_lm.py:145-176), blocks
+       ``>= cfg.n_layers`` are dropped (flamingo_mpt.py:198-246 deletes them), ``transformer.wte.weight`` is cut to
+       ``cfg.vocab`` rows (``resize_token_embeddings(len(tokenizer))``, factory.py:159; growing is refused because HF
+       initialises new rows randomly);
+    3. ``open_flamingo``: the OpenFlamingo ``checkpoint.pt`` (perceiver, gated x-attn layers, trained embeddings), loaded with
+       ``strict=False`` (eval_calvin.py:541-543) -- ``lang_encoder.gated_cross_attn_layers.i.*`` is the same module as
+       ``lang_encoder.transformer.blocks.i.gated_cross_attn_layer.*`` and is stored under the latter name;
+    4. ``deer``: a DeeR ``.pth`` (or its ``model_state_dict``), ``module.`` stripped, ``strict=False`` (eval_calvin.py:577).
+
+    Later sources override earlier ones.  Returns (state dict restricted to the tensors the engine needs, missing names)."""
+    from .weights import state_dict_spec
+    out: Dict[str, Any] = {}
+    if clip is not None:
+        for k, v in state_dict_of(clip).items():
+            k = _strip_module(k)
+            if k.startswith("visual."):
+                out["vision_encoder." + k[len("visual."):]] = v
+            elif k.startswith("vision_encoder."):
+                out[k] = v
+    if hf_lm is not None:
+        for k, v in state_dict_of(hf_lm).items():
+            k = _strip_module(k)
+            m = _HF_BLOCK.match(k)
+            if m:
+                if int(m.group(1)) < cfg.n_layers:
+                    out[f"lang_encoder.transformer.blocks.{m.group(1)}.decoder_layer.{m.group(2)}"] = v
+            elif k == "transformer.wte.weight":
+                if v.shape[0] < cfg.vocab:
+                    raise ValueError(f"embedding has {v.shape[0]} rows < vocab {cfg.vocab}: new rows would be random (factory.py:159)")
+                out["lang_encoder.transformer.wte.weight"] = v[: cfg.vocab]
+            elif k.startswith("transformer."):
+                out["lang_encoder." + k] = v
+    for src in (open_flamingo, deer):
+        if src is None:
+            continue
+        for k, v in state_dict_of(src).items():
+            k = _strip_module(k)
+            m = _XATTN_ALIAS.match(k)
+            if m:
+                k = f"lang_encoder.transformer.blocks.{m.group(1)}.gated_cross_attn_layer.{m.group(2)}"
+            out[k] = v
+    need = [n for n, _, _ in state_dict_spec(cfg)]
+    missing = [n for n in need if n not in out]
+    return {n: out[n] for n in need if n in out}, missing

@@ -1133,7 +1133,10 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
         KLAUNCH_CHECK("commit_pending");
         break;
       }
-      continue;                               // nobody leaves before the last layer: no compaction
+      // nobody leaves before the last layer: no compaction, only action_list[-1] moves on (value_net.py:127)
+      copy_pose_kernel<<<(n * 6 + 127) / 128, 128, 0, s.st>>>(c->cur_pose, c->meta[s.cur].prev_pose, n, s.nact());
+      KLAUNCH_CHECK("copy_pose");
+      continue;
     }
     commit_state_kernel<<<dim3(n, f.lstm_layers), 256, 0, s.st>>>(c->exit_flag, c->meta[s.cur].slot, c->cand_h, c->cand_c, c->h_state, c->c_state,
                                                                f.lstm_layers, f.lstm_hidden, f.max_batch, n, c->n_active + s.cur);

@@ -130,3 +130,41 @@ def test_checkpoint_name_and_hyperparameter_readout():
         config_from_checkpoint({}, name)                     # an old-style head (no LayerNorm, 3 hidden layers) is out of scope
     with pytest.raises(NotImplementedError):
         config_from_checkpoint(ck, name.replace("traj_cons", "state"))
+
+
+def test_assemble_state_dict_from_published_pieces():
+    """HF MPT + open_clip + OpenFlamingo + DeeR pieces with their native key names -> the model's state dict (f3)."""
+    import torch
+    from deer_vla_b200 import config_tiny
+    from deer_vla_b200.checkpoint import assemble_state_dict
+    from deer_vla_b200.weights import synth_state_dict
+    cfg = config_tiny()
+    full = synth_state_dict(cfg, 3)
+    hf, clip, of, deer = {}, {"text_projection": torch.zeros(2), "logit_scale": torch.zeros(())}, {}, {}
+    for k, v in full.items():
+        if k.startswith("vision_encoder."):
+            clip["visual." + k[len("vision_encoder."):]] = v
+        elif ".decoder_layer." in k:
+            i = k.split(".")[3]
+            hf[f"transformer.blocks.{i}." + k.split(".decoder_layer.")[1]] = v
+        elif k == "lang_encoder.transformer.wte.weight":
+            hf["transformer.wte.weight"] = torch.cat([v, torch.zeros(24, v.shape[1])])         # HF vocab is larger (50432 vs 50280)
+            of[k] = v + 1.0                                                                     # OpenFlamingo trains the new tokens' rows
+        elif ".gated_cross_attn_layer." in k:
+            i = k.split(".")[3]
+            of[f"lang_encoder.gated_cross_attn_layers.{i}." + k.split(".gated_cross_attn_layer.")[1]] = v
+        elif k.startswith("perceiver."):
+            of[k] = v * 0.5
+            deer["module." + k] = v                                                             # DeeR fine-tunes the resampler: later source wins
+        else:
+            deer["module." + k] = v
+    hf["transformer.blocks.99.ln_1.weight"] = torch.zeros(4)                                    # deeper blocks are deleted by the model
+    hf["transformer.ln_f.weight"] = torch.zeros(4)
+    merged, missing = assemble_state_dict(cfg, hf_lm=hf, clip=clip, open_flamingo=of, deer={"model_state_dict": deer, "exit_interval": 2})
+    assert missing == []
+    assert set(merged) == set(full)
+    for k, v in full.items():
+        want = v + 1.0 if k == "lang_encoder.transformer.wte.weight" else v
+        assert torch.equal(merged[k], want), k
+    _, missing = assemble_state_dict(cfg, hf_lm=hf, clip=clip)
+    assert any(m.startswith("perceiver.") for m in missing) and any(m.startswith("extra_exit.") for m in missing)
