@@ -375,7 +375,7 @@ def main():
     ap.add_argument("--batch", type=int, default=224, help="concurrent episodes per GPU")
     ap.add_argument("--seq", type=int, default=32)
     ap.add_argument("--calib-steps", type=int, default=8)
-    ap.add_argument("--cpu-steps", type=int, default=8, help="batch-1 oracle steps timed for cpu_baseline")
+    ap.add_argument("--cpu-steps", type=int, default=24, help="batch-1 oracle steps timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true", help="replay each step as one CUDA graph with conditional exit nodes (latency mode)")
     a = ap.parse_args()

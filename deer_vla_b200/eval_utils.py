@@ -3,8 +3,9 @@
 ``step(obs, goal)`` keeps the reference contract -- uint8 camera frames + an instruction string in, a
 ``(multi_execution, 7)`` float16 numpy action out -- and ``reset()`` clears the episode's LSTM state.
 ``BatchedModelWrapper`` steps N environments in lock-step through one engine call (slots = environments).
-Image preprocessing here is the open_clip transform restated in torch (bicubic resize to 224, center crop,
-CLIP mean/std); it is outside the device-timed hot path.
+Host-side image preprocessing is the open_clip transform (Pillow bicubic resize to 224, center crop, /255, CLIP mean/std);
+``BatchedModelWrapper(device_transform=True)`` and ``DeerEngine.step_u8`` run the same transform, bit-exactly, on the GPU
+(SURVEY §8 f1).
 """
 from __future__ import annotations
 
@@ -22,7 +23,25 @@ def clip_image_transform(image_size: int = 224) -> Callable:
     mean = torch.tensor(CLIP_MEAN).view(3, 1, 1)
     std = torch.tensor(CLIP_STD).view(3, 1, 1)
 
+    try:
+        from PIL import Image
+    except ImportError:                       # no Pillow: antialiased torch bicubic (close to, not identical with, the reference)
+        Image = None
+
+    def fn_pil(img) -> torch.Tensor:
+        # torchvision Resize(size, BICUBIC) -> CenterCrop(size) -> ToTensor -> Normalize, which is what open_clip composes
+        im = img if isinstance(img, Image.Image) else Image.fromarray(np.asarray(img, dtype=np.uint8))
+        w, h = im.size
+        nh, nw = (image_size, int(image_size * w / h)) if h <= w else (int(image_size * h / w), image_size)
+        if (nw, nh) != (w, h):
+            im = im.resize((nw, nh), Image.BICUBIC)
+        t, l = int(round((nh - image_size) / 2.0)), int(round((nw - image_size) / 2.0))
+        a = torch.from_numpy(np.asarray(im.convert("RGB"))[t:t + image_size, l:l + image_size].copy()).permute(2, 0, 1).float().div(255)
+        return ((a - mean) / std).contiguous()
+
     def fn(img) -> torch.Tensor:
+        if Image is not None:
+            return fn_pil(img)
         a = torch.from_numpy(np.asarray(img)).permute(2, 0, 1).float().unsqueeze(0) / 255.0
         h, w = a.shape[-2:]
         s = image_size / min(h, w)
@@ -95,8 +114,11 @@ class BatchedModelWrapper:
     """N environments in lock-step: one ``deer_step`` per environment step.  ``reset(i)`` clears one env's
     LSTM slot (a new subtask rollout, eval_utils.py:646)."""
 
-    def __init__(self, model, tokenizer, image_processor, exit_controller=None, multi_execution=1):
+    def __init__(self, model, tokenizer, image_processor, exit_controller=None, multi_execution=1, device_transform=False):
+        """``device_transform=True``: the raw uint8 camera frames go to the GPU as they are and the open_clip transform
+        (Pillow-exact bicubic resize + normalise) runs there (``deer_step_host_u8``); ``image_processor`` is then unused."""
         self.model, self.exit_controller, self.multi_execution = model, exit_controller, multi_execution
+        self.device_transform = device_transform
         self.text_process_fn = lambda goals: preprocess_text_calvin(goals, tokenizer)
         self.image_process_fn = lambda imgs: preprocess_image(imgs, image_processor)
         self.device = model.module.engine.device
@@ -107,6 +129,19 @@ class BatchedModelWrapper:
 
     def step(self, obs_list, goals: Sequence[str], env_ids: Optional[Sequence[int]] = None) -> np.ndarray:
         n = len(obs_list)
+        if self.device_transform:
+            eng = self.model.module.engine
+            if self.exit_controller is not None:
+                assert self.exit_controller.thresholds is not None, "Please set thresholds before calling forward"     # value_net.py:279
+            rgb8 = torch.from_numpy(np.stack([np.asarray(o["rgb_obs"]["rgb_static"], dtype=np.uint8) for o in obs_list]))
+            grip8 = torch.from_numpy(np.stack([np.asarray(o["rgb_obs"]["rgb_gripper"], dtype=np.uint8) for o in obs_list]))
+            ids, mask = self.text_process_fn(list(goals))
+            slots = None if env_ids is None else torch.tensor(list(env_ids), dtype=torch.int32)
+            out = eng.step_u8(rgb8, grip8, ids, mask.to(torch.uint8), slots,
+                              exit_id=None if self.exit_controller is not None else eng.cfg.n_layers - 1)
+            self.current_exit_layers = out["exit_layer"].tolist()
+            a = out["action"].clone()
+            return torch.stack([a] * self.multi_execution, dim=1).to(torch.float16).numpy()
         rgb = self.image_process_fn([o["rgb_obs"]["rgb_static"] for o in obs_list]).view(n, 1, 1, 3, *([self.model.module.cfg.image_size] * 2))
         grip = self.image_process_fn([o["rgb_obs"]["rgb_gripper"] for o in obs_list]).view(n, 1, 1, 3, *([self.model.module.cfg.image_size] * 2))
         ids, mask = self.text_process_fn(list(goals))

@@ -151,3 +151,26 @@ def test_calls_on_different_streams_are_ordered():
             assert torch.equal(got["exit_layer"].cpu(), want["exit_layer"]), rep
             assert torch.equal(got["action"].cpu(), want["action"]), rep
     eng.close()
+
+
+def test_batched_wrapper_device_transform_equals_host_transform():
+    """Raw uint8 frames transformed on the GPU (deer_step_host_u8) vs the Pillow transform on the host: the transform is
+    bit-exact, so actions and exits are identical."""
+    pytest.importorskip("PIL.Image")
+    from deer_vla_b200.eval_utils import BatchedModelWrapper, clip_image_transform
+    ocfg, W, eng, model, ctrl = _build(max_batch=3)
+    ctrl._set_threshold_value([0.3, 0.25, 1e8])
+    tok, proc = _Tok(ocfg), clip_image_transform(ocfg.image_size)
+    host = BatchedModelWrapper(model, tok, proc, exit_controller=ctrl)
+    dev = BatchedModelWrapper(model, tok, None, exit_controller=ctrl, device_transform=True)
+    goals = ["open the drawer", "lift the pink block from the table", "turn on the led"]
+    rs = np.random.RandomState(4)
+    obs_seq = [[{"rgb_obs": {"rgb_static": (rs.rand(200, 200, 3) * 255).astype(np.uint8),
+                             "rgb_gripper": (rs.rand(84, 84, 3) * 255).astype(np.uint8)}} for _ in goals] for _ in range(3)]
+    res = []
+    for w in (host, dev):
+        w.reset()
+        res.append([(w.step(obs, goals).copy(), list(w.current_exit_layers)) for obs in obs_seq])
+    for (a0, e0), (a1, e1) in zip(*res):
+        assert e0 == e1 and np.array_equal(a0, a1)
+    eng.close()

@@ -34,6 +34,15 @@ def test_restatement_matches_live_pillow():
         assert np.array_equal(R.resize_bicubic_u8(img, oh, ow), ref)
 
 
+def test_product_host_transform_is_the_reference_transform():
+    """deer_vla_b200.eval_utils.clip_image_transform (Pillow path) == the restatement == torchvision's composition."""
+    pytest.importorskip("PIL.Image")
+    from deer_vla_b200.eval_utils import clip_image_transform
+    for seed, (h, w, s) in enumerate([(200, 200, 224), (84, 84, 224), (120, 300, 56), (300, 120, 56)]):
+        img = frames(seed + 50, h, w)
+        assert np.array_equal(clip_image_transform(s)(img).numpy(), R.clip_transform(img, s)), (h, w, s)
+
+
 def test_coefficients_are_normalised():
     for a, b in [(200, 224), (84, 224), (500, 224), (224, 224)]:
         bounds, kk, ksize = R.precompute_coeffs(a, b)
