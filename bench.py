@@ -61,6 +61,15 @@ def algorithmic_gflop_per_step(cfg, S: int, exit_layer: int, exit_rank: int) -> 
     return 2.0 * (2 * vit + 2 * perc + layers + (exit_rank + 3) * head) / 1e9
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -150,7 +159,7 @@ def reference_arm(a):
             "cpu_baseline": {"value": r["value"], "unit": "action-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "action-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "exit_layers": r["exits"]}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -357,7 +366,7 @@ def engine_arm(a):
                 "mean_exit_depth_layers": float(sum((e + 1) * exit_hist[e] for e in exits_sorted) / max(1, total_steps)),
                 "step_algorithmic_tflops": step_tflops, "weights_load_s": t_load,
                 "gathered_rows": int(gathered.shape[0])}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -379,6 +388,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true", help="replay each step as one CUDA graph with conditional exit nodes (latency mode)")
     a = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): anything a library prints there (e.g. NCCL's version banner) goes to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         reference_arm(a)
     else:
