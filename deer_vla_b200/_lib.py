@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdeer_engine.so")
+LIB_PATH = os.environ.get("DEER_LIB") or os.path.join(_HERE, "libdeer_engine.so")   # DEER_LIB: an instrumented build (scripts/)
 
 ABI_VERSION = 1
 PREC_BF16, PREC_FP32 = 0, 1

@@ -148,6 +148,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// A/B switches of the attention kernel's barrier flavour (see scripts/gpu_exp3.sh)
+#ifdef DEER_ATTN_RELAXED
+#define ATT_ARRIVE(bar) mbar_arrive_relaxed(bar)
+#else
+#define ATT_ARRIVE(bar) mbar_arrive(bar)
+#endif
+#ifdef DEER_ATTN_SPIN
+#define ATT_WAIT(bar, ph) mbar_wait_spin(bar, ph)
+#else
+#define ATT_WAIT(bar, ph) mbar_wait(bar, ph)
+#endif
+
 struct AttnTc {
   static constexpr int SKP = 272;                        // rows staged per K / V buffer (17 x 16)
   static constexpr int NMMA = 256;                       // keys that go through the tensor core
@@ -157,10 +169,12 @@ struct AttnTc {
   static constexpr int HALF_ROWS = 136, HALF_BYTES = HALF_ROWS * 128;
   static constexpr int Q_BYTES = 128 * 128;
   static constexpr int OFF_K = 0, OFF_V = 2 * KV_BYTES, OFF_Q = 4 * KV_BYTES, OFF_P = OFF_Q + 2 * Q_BYTES;   // OFF_P: fp32 scratch of the spare warp
-  static constexpr int OFF_XMAX = OFF_P + SKP * 4 + 64;          // [2 buf][2 half][128]
-  static constexpr int OFF_XSUM = OFF_XMAX + 2 * 2 * 128 * 4;    // [2 buf][2 half][128]
+  static constexpr int OFF_XMAX = OFF_P + SKP * 4 + 64;          // [2 buf][4 stages][2 half][128]
+  static constexpr int OFF_XSUM = OFF_XMAX + 2 * 4 * 2 * 128 * 4;  // [2 buf][2 half][128]
   static constexpr int OFF_XTAIL = OFF_XSUM + 2 * 2 * 128 * 4;   // [2 buf][16][128]
-  static constexpr int OFF_BAR = OFF_XTAIL + 2 * MAX_TAIL * 128 * 4;
+  static constexpr int OST_ROW = 80;                             // bytes per staged output row (64 B of bf16 + pad: conflict-free uint4 writes)
+  static constexpr int OFF_OST = OFF_XTAIL + 2 * MAX_TAIL * 128 * 4;   // [8 warps][32 rows][OST_ROW]
+  static constexpr int OFF_BAR = OFF_OST + 8 * 32 * OST_ROW;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static constexpr int THREADS = 11 * 32;
   static constexpr int TMEM_COLS = 512;
@@ -184,6 +198,7 @@ __device__ __forceinline__ float dot64_swz(const uint8_t* a_tile, int ra, const 
   return acc;
 }
 
+template <int VER>      // 3 = whole-row softmax (read 128 scores, then exp), 4 = chunk-pipelined softmax (the default)
 __global__ void __launch_bounds__(AttnTc::THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                const bf16* __restrict__ Qg, int ldq, bf16* __restrict__ Og, int ldo, int B, int H, int Sq, int Sk, float scale_log2,
@@ -234,6 +249,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -242,7 +259,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int it = blockIdx.x + is * gridDim.x;
         const int b = it / H, h = it % H;
         const int kb = is & 1;
-        mbar_wait(&kv_empty[kb], ((is >> 1) & 1) ^ 1u);
+        ATT_WAIT(&kv_empty[kb], ((is >> 1) & 1) ^ 1u);
         mbar_arrive_expect_tx(&kv_full[kb], 2 * A::KV_BYTES);
         uint8_t* sk = smem + A::OFF_K + kb * A::KV_BYTES;
         uint8_t* sv = smem + A::OFF_V + kb * A::KV_BYTES;
@@ -252,7 +269,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tma_load_2d(sv + A::HALF_BYTES, &tmV, &kv_full[kb], h * 64, b * Sk + A::HALF_ROWS);
         for (int t = 0; t < n_sub; ++t) {
           const int n = is * n_sub + t, qb = n & 1;
-          mbar_wait(&q_empty[qb], ((n >> 1) & 1) ^ 1u);
+          ATT_WAIT(&q_empty[qb], ((n >> 1) & 1) ^ 1u);
           mbar_arrive_expect_tx(&q_full[qb], A::Q_BYTES);
           tma_load_2d(smem + A::OFF_Q + qb * A::Q_BYTES, &tmQ, &q_full[qb], h * 64, b * Sq + t * 128);
         }
@@ -265,9 +282,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       constexpr uint32_t idesc_pv = make_idesc_bf16_major(128, 64, 0, 1);     // B = V, MN-major
       auto issue_qk = [&](int n) {
         const int is = n / n_sub, t = n % n_sub, kb = is & 1, qb = n & 1, u = n & 1;
-        if (t == 0) mbar_wait(&kv_full[kb], (is >> 1) & 1);
-        mbar_wait(&q_full[qb], (n >> 1) & 1);
-        if (n >= 2) mbar_wait(&o_empty[u], ((n >> 1) - 1) & 1);        // the buffer's previous tile has been drained
+        if (t == 0) ATT_WAIT(&kv_full[kb], (is >> 1) & 1);
+        ATT_WAIT(&q_full[qb], (n >> 1) & 1);
+        if (n >= 2) ATT_WAIT(&o_empty[u], ((n >> 1) - 1) & 1);        // the buffer's previous tile has been drained
         tc_fence_after();
         const uint32_t q_addr = smem_u32(smem + A::OFF_Q + qb * A::Q_BYTES);
         const uint32_t k_addr = smem_u32(smem + A::OFF_K + kb * A::KV_BYTES);
@@ -282,7 +299,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int n = 0; n < total; ++n) {
         if (n + 1 < total) issue_qk(n + 1);
         const int is = n / n_sub, t = n % n_sub, kb = is & 1, u = n & 1;
-        mbar_wait(&p_full[u], (n >> 1) & 1);
+        ATT_WAIT(&p_full[u], (n >> 1) & 1);
         tc_fence_after();
         const uint32_t v_addr = smem_u32(smem + A::OFF_V + kb * A::KV_BYTES);
 #pragma unroll 1
@@ -317,13 +334,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int is = n / n_sub, t = n % n_sub, kb = is & 1, u = n & 1;
       const int it = blockIdx.x + is * gridDim.x;
       const int b = it / H, h = it % H;
-      mbar_wait(&o_full[u], (n >> 1) & 1);
+      ATT_WAIT(&o_full[u], (n >> 1) & 1);
       tc_fence_after();
       TICK(5);
       const float inv = 1.0f / (xsum[(u * 2 + 0) * 128 + rloc] + xsum[(u * 2 + 1) * 128 + rloc]);
       const uint8_t* sv = smem + A::OFF_V + kb * A::KV_BYTES;
-      const int row = t * 128 + rloc;
-      bf16* orow = Og + (static_cast<size_t>(b) * Sq + row) * ldo + h * 64 + hf * 32;
+      uint8_t* ost = smem + A::OFF_OST + (warp - 2) * (32 * A::OST_ROW);
 #pragma unroll 1
       for (int hh = 0; hh < 2; ++hh) {                     // 16 O columns at a time (keeps the register peak down)
         float v[16];
@@ -344,21 +360,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
           }
         }
-        if (row < Sq) {
+        // this lane's row -> its slot of the warp's staging tile (a lane owns one ROW here; the stores below want rows contiguous)
 #pragma unroll
-          for (int j = 0; j < 16; j += 8) {
-            uint4 o;
-            o.x = pack_bf16x2(v[j] * inv, v[j + 1] * inv); o.y = pack_bf16x2(v[j + 2] * inv, v[j + 3] * inv);
-            o.z = pack_bf16x2(v[j + 4] * inv, v[j + 5] * inv); o.w = pack_bf16x2(v[j + 6] * inv, v[j + 7] * inv);
-            *reinterpret_cast<uint4*>(orow + hh * 16 + j) = o;
-          }
+        for (int j = 0; j < 16; j += 8) {
+          uint4 o;
+          o.x = pack_bf16x2(v[j] * inv, v[j + 1] * inv); o.y = pack_bf16x2(v[j + 2] * inv, v[j + 3] * inv);
+          o.z = pack_bf16x2(v[j + 4] * inv, v[j + 5] * inv); o.w = pack_bf16x2(v[j + 6] * inv, v[j + 7] * inv);
+          *reinterpret_cast<uint4*>(ost + lane * A::OST_ROW + hh * 32 + j * 2) = o;
+        }
+      }
+      __syncwarp();
+      // coalesced stores: 4 lanes cover the 64 contiguous bytes this warp owns of a row, 8 rows per instruction (a lane-per-row
+      // store touched 32 different 128-byte lines per instruction and made the epilogue the longest phase of a tile)
+      {
+        const int ch = lane & 3, rsub = lane >> 2;
+        bf16* obase = Og + (static_cast<size_t>(b) * Sq + t * 128 + qd * 32) * ldo + h * 64 + hf * 32 + ch * 8;
+#pragma unroll
+        for (int itr = 0; itr < 4; ++itr) {
+          const int r = itr * 8 + rsub;
+          const uint4 o = *reinterpret_cast<const uint4*>(ost + r * A::OST_ROW + ch * 16);
+          if (t * 128 + qd * 32 + r < Sq) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(r) * ldo) = o;
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&o_empty[u]);
-        if (t == n_sub - 1) mbar_arrive(&kv_empty[kb]);
+        ATT_ARRIVE(&o_empty[u]);
+        if (t == n_sub - 1) ATT_ARRIVE(&kv_empty[kb]);
       }
     };
 
@@ -371,10 +399,104 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         break;
       }
       const int is = n / n_sub, kb = is & 1, qb = n & 1, u = n & 1;
-      mbar_wait(&s_full[u], (n >> 1) & 1);
+      ATT_WAIT(&s_full[u], (n >> 1) & 1);
       tc_fence_after();
       TICK(0);
-      // ---- this thread's 128 scores, read ONCE
+      if (VER == 4) {
+        // ---- chunk-pipelined softmax.  The 128 scores of this thread arrive as four 32-column chunks; chunk k+1 is in flight
+        // (tcgen05.ld is asynchronous until wait::ld) while chunk k goes through max -> exp2 -> pack, so the ~64 B/clk tensor-memory
+        // read port and the MUFU pipe work at the same time instead of one after the other.
+        // Exactness without the full-row max: probabilities are taken relative to a running reference r_k (scaled log2 domain),
+        //   r_0 = max(stage-0 chunk of both halves, tail keys),   r_k = max(r_{k-1}, M_k - 30k)   (M_k = stage-k chunk max),
+        // identical in the two warps that share a row (they exchange M_k through smem at every stage).  Stored p <= 2^(30k) <= 2^90;
+        // if r_k moves, everything stored before is <= 2^(30(k-1)) against a new top term of exactly 2^(30k): the stale terms
+        // carry <= 256 * 2^-30 = 2^-22 of the row's mass, i.e. the softmax is exact to fp32 rounding, with no second pass.
+        const uint32_t ts = tmem_base + lane_off + static_cast<uint32_t>(256 * u + 128 * hf);
+        const int c0 = 128 * hf;
+        float sa[32], sb[32];
+        uint32_t pk[64];
+        tmem_ld_32x32(ts, sa);
+        float m = -INFINITY;
+        if (hf == 1) {
+          const uint8_t* sq = smem + A::OFF_Q + qb * A::Q_BYTES;
+          const uint8_t* sk = smem + A::OFF_K + kb * A::KV_BYTES;
+#pragma unroll 1
+          for (int j = 0; j < n_tail; ++j) {
+            const float sj = dot64_swz(sq, rloc, sk, A::NMMA + j);
+            xtail[(u * A::MAX_TAIL + j) * 128 + rloc] = sj;
+            m = fmaxf(m, sj);
+          }
+          __syncwarp();
+          if (lane == 0) ATT_ARRIVE(&q_empty[qb]);
+        }
+        tmem_ld_wait();
+        tmem_ld_32x32(ts + 32u, sb);
+        TICK(6);
+        float* xm = xmax + u * (4 * 2 * 128);
+        float ref = 0.0f, l = 0.0f;
+#define STAGE_MAX(SX, K, MINIT)                                                                              \
+        {                                                                                                    \
+          if (c0 + 32 * ((K) + 1) > n_mma) {                                                                 \
+            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (c0 + 32 * (K) + j >= n_mma) SX[j] = -INFINITY; \
+          }                                                                                                  \
+          float cm = (MINIT);                                                                                \
+          _Pragma("unroll") for (int j = 0; j < 32; j += 2) cm = fmaxf(cm, fmaxf(SX[j], SX[j + 1]));         \
+          xm[((K) * 2 + hf) * 128 + rloc] = cm;                                                              \
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");                                         \
+          cm = fmaxf(cm, xm[((K) * 2 + (hf ^ 1)) * 128 + rloc]) * scale_log2;                                \
+          ref = ((K) == 0) ? cm : fmaxf(ref, cm - 30.0f * (K));                                              \
+        }
+#define STAGE_EXP(SX, K)                                                                                     \
+        {                                                                                                    \
+          _Pragma("unroll") for (int j = 0; j < 32; j += 2) {                                                \
+            const float p0 = ex2_approx(fmaf(SX[j], scale_log2, -ref)), p1 = ex2_approx(fmaf(SX[j + 1], scale_log2, -ref)); \
+            l += p0 + p1;                                                                                    \
+            pk[(K) * 16 + (j >> 1)] = pack_bf16x2(p0, p1);                                                   \
+          }                                                                                                  \
+        }
+        STAGE_MAX(sa, 0, m)
+        STAGE_EXP(sa, 0)
+        tmem_ld_wait();
+        tmem_ld_32x32(ts + 64u, sa);
+        STAGE_MAX(sb, 1, -INFINITY)
+        TICK(1);
+        if (n > 0) epilogue(n - 1);         // PV(n-1) has had two stages to finish; frees the other TMEM buffer for QK(n+1),
+        TICK(2);                            // which still has two stages of this tile to complete in
+        STAGE_EXP(sb, 1)
+        tmem_ld_wait();
+        tmem_ld_32x32(ts + 96u, sb);
+        STAGE_MAX(sa, 2, -INFINITY)
+        STAGE_EXP(sa, 2)
+        tmem_ld_wait();
+        STAGE_MAX(sb, 3, -INFINITY)         // after this stage's bar.sync BOTH warps of the quarter have read all their scores:
+        STAGE_EXP(sb, 3)                    // P may now overwrite the score columns in place
+#undef STAGE_MAX
+#undef STAGE_EXP
+        const uint32_t tp = tmem_base + lane_off + static_cast<uint32_t>(256 * u + 64 * hf);
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          uint32_t q16[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) q16[j] = pk[ci * 16 + j];
+          tmem_st_32x32b_x16(tp + static_cast<uint32_t>(ci * 16), q16);
+        }
+        if (hf == 1) {
+#pragma unroll 1
+          for (int j = 0; j < n_tail; ++j) {
+            const float pj = ex2_approx(fmaf(xtail[(u * A::MAX_TAIL + j) * 128 + rloc], scale_log2, -ref));
+            l += pj;
+            xtail[(u * A::MAX_TAIL + j) * 128 + rloc] = pj;
+          }
+        }
+        xsum[(u * 2 + hf) * 128 + rloc] = l;
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ATT_ARRIVE(&p_full[u]);
+        TICK(3);
+        continue;
+      }
+      // ---- (VER 3) this thread's 128 scores, read ONCE
       const uint32_t ts = tmem_base + lane_off + static_cast<uint32_t>(256 * u + 128 * hf);
       float s0[32], s1[32], s2[32], s3[32];
       tmem_ld_32x32(ts, s0);
@@ -393,7 +515,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           m = fmaxf(m, sj);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&q_empty[qb]);
+        if (lane == 0) ATT_ARRIVE(&q_empty[qb]);
       }
       tmem_ld_wait();
       TICK(6);
@@ -409,9 +531,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) m = fmaxf(fmaxf(m, s0[j]), fmaxf(fmaxf(s1[j], s2[j]), s3[j]));
-      xmax[(u * 2 + hf) * 128 + rloc] = m;
+      xmax[(u * 8 + hf) * 128 + rloc] = m;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");     // partner's max is visible AND both halves of S have been read
-      m = fmaxf(m, xmax[(u * 2 + (hf ^ 1)) * 128 + rloc]);
+      m = fmaxf(m, xmax[(u * 8 + (hf ^ 1)) * 128 + rloc]);
       const float ms = m * scale_log2;
       TICK(1);
       // ---- the previous tile's epilogue goes here: its PV finished while we were reading scores
@@ -447,7 +569,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[u]);
+      if (lane == 0) ATT_ARRIVE(&p_full[u]);
       TICK(3);
     }
     TICK(4);
@@ -461,7 +583,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int is = 0; is < my_items; ++is) {
       const int it = blockIdx.x + is * gridDim.x;
       const int b = it / H, h = it % H, kb = is & 1;
-      mbar_wait(&kv_full[kb], (is >> 1) & 1);
+      ATT_WAIT(&kv_full[kb], (is >> 1) & 1);
       const uint8_t* sK = smem + A::OFF_K + kb * A::KV_BYTES;
       const uint8_t* sV = smem + A::OFF_V + kb * A::KV_BYTES;
       for (int r = 0; r < side_rows; ++r) {
@@ -511,7 +633,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         __syncwarp();
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&kv_empty[kb]);
+      if (lane == 0) ATT_ARRIVE(&kv_empty[kb]);
     }
   }
   tc_fence_before();

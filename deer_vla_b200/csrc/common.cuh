@@ -66,6 +66,15 @@ template <int ACT> __device__ __forceinline__ float act_fast(float v) {
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is
+// still draining: its prologue (barrier init, TMEM allocation, tensormap prefetch) overlaps the predecessor's tail.  pdl_wait()
+// blocks until the predecessor grid has completed and its writes are visible -- it must precede the first global access that
+// depends on earlier work (including the device-side row count); without the launch attribute it returns immediately.
+// pdl_trigger() lets the NEXT kernel's CTAs be scheduled as soon as this grid's CTAs free their SM resources.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- warp / block reductions ---------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -3,6 +3,7 @@
 #include "../../include/deer_engine.h"
 #include "attention.cuh"
 #include "attn_tc.cuh"
+#include "attn_tc5.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
 
@@ -60,6 +61,20 @@ static bool make_tmap(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t 
   return r == CUDA_SUCCESS;
 }
 
+// Launch with (optionally) programmatic stream serialization: the kernel may begin while its predecessor drains; the kernels
+// launched this way all start with pdl_wait() (common.cuh).  DEER_PDL=0 turns it off (A/B), and it is never used during graph capture.
+static bool g_pdl_env = getenv("DEER_PDL") ? atoi(getenv("DEER_PDL")) != 0 : true;
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (pdl && g_pdl_env) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 struct TmapKey {
   const void* p; uint64_t rows, cols, ld; uint32_t box;
   bool operator<(const TmapKey& o) const { return std::tie(p, rows, cols, ld, box) < std::tie(o.p, o.rows, o.cols, o.ld, o.box); }
@@ -79,6 +94,7 @@ struct GemmCtx {
   bool attr_set[4] = {false, false, false, false};
   LaunchStats* stats = nullptr;
   std::string* err = nullptr;
+  bool pdl = false;            // programmatic dependent launch allowed (off while a CUDA graph is being captured)
   // profiling
   bool profile = false;
   int tag = 0, epoch = 0;
@@ -101,8 +117,7 @@ static cudaError_t launch_tc(GemmCtx& g, const CUtensorMap& ta, const CUtensorMa
   }
   const int tiles = ((M + 127) / 128) * ((N + BN - 1) / BN);
   const int grid = std::max(1, std::min(tiles, DEER_NUM_SMS));
-  gemm_tc_kernel<BN><<<grid, G::THREADS, G::SMEM_BYTES, st>>>(ta, tb, M, m_dev, m_mul, N, K, epi);
-  return cudaGetLastError();
+  return launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(G::THREADS), G::SMEM_BYTES, st, g.pdl, ta, tb, M, m_dev, m_mul, N, K, epi);
 }
 
 static cudaError_t launch_tc2(GemmCtx& g, const CUtensorMap& ta, const CUtensorMap& tb, int M, const int* m_dev, int m_mul, int N, int K,
@@ -115,8 +130,7 @@ static cudaError_t launch_tc2(GemmCtx& g, const CUtensorMap& ta, const CUtensorM
   }
   const int tiles = ((M + 255) / 256) * ((N + 255) / 256);
   const int clusters = std::max(1, std::min(tiles, DEER_NUM_SMS / 2));
-  gemm_tc2_kernel<<<2 * clusters, G::THREADS, G::SMEM_BYTES, st>>>(ta, tb, M, m_dev, m_mul, N, K, epi);
-  return cudaGetLastError();
+  return launch_k(gemm_tc2_kernel, dim3(2 * clusters), dim3(G::THREADS), G::SMEM_BYTES, st, g.pdl, ta, tb, M, m_dev, m_mul, N, K, epi);
 }
 
 // dtype: 0 bf16, 1 fp32.  impl: DEER_GEMM_* (2 = force the 1-CTA tcgen05 kernel, for A/B comparisons).  a_rows: allocated rows of A (>= M) for the TMA bounds.
@@ -190,7 +204,7 @@ static const CUtensorMap* attn_tmap(const void* ptr, uint64_t rows, uint64_t col
 
 // impl: 0 = tensor-core path (tcgen05 kernel when the shape allows, else the mma.sync flash kernel), 1 = SIMT reference,
 //       2 = on-chip small-attention kernel (LLM layers), 3 = force the mma.sync flash kernel
-static int run_attention(int impl, int dtype, const AttnParams& p, std::string* err, LaunchStats* stats, cudaStream_t st) {
+static int run_attention(int impl, int dtype, const AttnParams& p, std::string* err, LaunchStats* stats, cudaStream_t st, bool pdl = false) {
   if (p.B_host <= 0) return DEER_OK;
   const bool plain = dtype == 0 && p.hd == 64 && !p.causal && !p.alibi_slopes && !p.kv_len && !p.qmode && !p.n_dev && p.ldk == p.ldv;
   static const bool no_tc = getenv("DEER_ATTN_NO_TC") != nullptr;
@@ -202,14 +216,19 @@ static int run_attention(int impl, int dtype, const AttnParams& p, std::string* 
     const CUtensorMap* tv = attn_tmap(p.V, (uint64_t)p.B_host * p.Sk, width, p.ldv, AttnTc::HALF_ROWS);
     if (tq && tk && tv) {
       static bool attr_done = false;
+      // schedule A/B switches: v5 (two independent softmax groups, one thread per row) is the product path
+      static const int ver = getenv("DEER_ATTN_V3") ? 3 : (getenv("DEER_ATTN_V4") ? 4 : 5);
       if (!attr_done) {
-        cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTc::SMEM_BYTES);
+        cudaFuncSetAttribute(attn_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTc::SMEM_BYTES);
+        cudaFuncSetAttribute(attn_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTc::SMEM_BYTES);
+        cudaFuncSetAttribute(attn_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTc5::SMEM_BYTES);
         attr_done = true;
       }
       const int grid = std::min(p.B_host * p.H, DEER_NUM_SMS);
-      attn_tc_kernel<<<grid, AttnTc::THREADS, AttnTc::SMEM_BYTES, st>>>(*tq, *tk, *tv, reinterpret_cast<const bf16*>(p.Q), p.ldq,
-                                                                        reinterpret_cast<bf16*>(p.O), p.ldo, p.B_host, p.H, p.Sq, p.Sk,
-                                                                        p.scale * 1.4426950408889634f, g_attn_dbg);
+      auto kern = (ver == 3) ? attn_tc_kernel<3> : (ver == 4 ? attn_tc_kernel<4> : attn_tc5_kernel);
+      const size_t smem_bytes = (ver == 5) ? AttnTc5::SMEM_BYTES : AttnTc::SMEM_BYTES;
+      launch_k(kern, dim3(grid), dim3(AttnTc::THREADS), smem_bytes, st, pdl, *tq, *tk, *tv, reinterpret_cast<const bf16*>(p.Q), p.ldq,
+               reinterpret_cast<bf16*>(p.O), p.ldo, p.B_host, p.H, p.Sq, p.Sk, p.scale * 1.4426950408889634f, g_attn_dbg);
       done = true;
     }
   }
@@ -881,7 +900,7 @@ template <typename T> struct StepImpl {
     const bool vec_ok = (D % 128 == 0) && (in_ld % 4 == 0) && (out_ld % 4 == 0) && (out2 == nullptr || out2_ld % 4 == 0);
     const int nvec = D / 128;
     const int wgrid = (rows + 3) / 4;
-#define LNW(NV) layernorm_warp_kernel<TIn, TOut, NV><<<wgrid, 128, 0, st>>>(in, in_ld, in_map, g, b, groups, out, out_ld, map, out2, out2_ld, relu, rows, n_dev, n_mul)
+#define LNW(NV) launch_k(layernorm_warp_kernel<TIn, TOut, NV>, dim3(wgrid), dim3(128), 0, st, c->gemm.pdl, in, in_ld, in_map, g, b, groups, out, out_ld, map, out2, out2_ld, relu, rows, n_dev, n_mul)
     if (vec_ok && nvec == 1) LNW(1);
     else if (vec_ok && nvec == 2) LNW(2);
     else if (vec_ok && nvec == 4) LNW(4);
@@ -922,7 +941,7 @@ template <typename T> struct StepImpl {
         AttnParams a{};
         a.Q = c->v_qkv; a.K = tp(c->v_qkv) + Wd; a.V = tp(c->v_qkv) + 2 * Wd; a.O = c->v_att;
         a.ldq = a.ldk = a.ldv = 3 * Wd; a.ldo = Wd; a.Sq = a.Sk = L; a.H = f.vit_heads; a.hd = 64; a.scale = 0.125f; a.B_host = nc;
-        RET(run_attention(0, c->dtype, a, &c->err, &c->stats, st));
+        RET(run_attention(0, c->dtype, a, &c->err, &c->stats, st, c->gemm.pdl));
         RET(gemm(c->v_att, Wd, Mmax, w.w_out, Wd, M, Wd, Wd, vxc, Wd, 1, w.b_out, ACT_NONE, nullptr, vxc, Wd, nullptr, 0));
         RET(ln<float, T>(vxc, Wd, w.ln2_g, w.ln2_b, 1, Wd, tp(c->v_ln), Wd, id, nullptr, 0, 0, M, nullptr, 0));
         RET(gemm(c->v_ln, Wd, Mmax, w.w_fc, Wd, M, f.vit_mlp, Wd, c->v_h, f.vit_mlp, 0, w.b_fc, ACT_QUICKGELU, nullptr, nullptr, 0, nullptr, 0));
@@ -1074,6 +1093,7 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
     cudaEventRecord(c->ev_step0, s.st);
   }
   c->gemm.tag = 0;
+  c->gemm.pdl = (c->cap_level < 0) && !c->gemm.profile;
   RET(s.vision(rgb, grip));
   c->gemm.tag = 2;
   if (c->dtype == 1) embed_kernel<float><<<n * S, 256, 0, s.st>>>(ids, reinterpret_cast<const float*>(c->wte), c->x[0], n * S, f.d_model, f.vocab);

@@ -44,6 +44,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // try_wait with a suspend-time hint: the thread SLEEPS in hardware until the phase flips or ~the hint (ns) expires, instead
 // of spinning.  (Without the hint the single-thread TMA / MMA roles' spin loops issued as many instructions as the math
 // warps sharing their scheduler -- visible as TRYWAIT/BRA/YIELD in the ncu instruction mix.)
+#ifndef DEER_WAIT_HINT_NS
+#define DEER_WAIT_HINT_NS 20000
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -53,9 +56,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(static_cast<uint32_t>(DEER_WAIT_HINT_NS))
       : "memory");
   return ok != 0;
+}
+// Relaxed arrive (CTA scope): the waiter only needs what the program already guarantees before the arrive (tcgen05 loads / stores
+// retired behind tcgen05.wait + fence::before_thread_sync, shared-memory reads consumed); the default .release would also hold the
+// arrive until this thread's earlier GLOBAL stores have drained.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// try_wait without a suspend-time hint: returns after the (short) implementation-defined window; for waits that sit on a critical
+// path of a few hundred cycles, where the wake-up latency of a long suspend would show.
+__device__ __forceinline__ bool mbar_try_wait_nohint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_nohint(bar, parity)) {
+    if (++spins > (1u << 28)) __trap();
+  }
 }
 // Bounded wait: a protocol bug must surface as a launch failure (trap), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -241,11 +271,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int M = dyn_rows(M_host, m_dev, m_mul);
-  const int m_blocks = (M + G::BM - 1) / G::BM;
-  const int n_blocks = (N + BN - 1) / BN;
-  const int num_tiles = m_blocks * n_blocks;
-  const int num_kb = (K + G::BK - 1) / G::BK;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -265,6 +290,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                           // everything above overlapped the previous kernel's tail
+  pdl_trigger();
+  const int M = dyn_rows(M_host, m_dev, m_mul);
+  const int m_blocks = (M + G::BM - 1) / G::BM;
+  const int n_blocks = (N + BN - 1) / BN;
+  const int num_tiles = m_blocks * n_blocks;
+  const int num_kb = (K + G::BK - 1) / G::BK;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -338,7 +370,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
+#ifdef DEER_ATTN_RELAXED
+      if (lane == 0) mbar_arrive_relaxed(&tempty_bar[as]);
+#else
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
+#endif
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
   }
@@ -514,11 +550,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = (rank == 0);
-  const int M = dyn_rows(M_host, m_dev, m_mul);
-  const int m_blocks = (M + G::BM - 1) / G::BM;
-  const int n_blocks = (N + G::BN - 1) / G::BN;
-  const int num_tiles = m_blocks * n_blocks;
-  const int num_kb = (K + G::BK - 1) / G::BK;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
@@ -539,6 +570,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                           // everything above overlapped the previous kernel's tail
+  pdl_trigger();
+  const int M = dyn_rows(M_host, m_dev, m_mul);
+  const int m_blocks = (M + G::BM - 1) / G::BM;
+  const int n_blocks = (N + G::BN - 1) / G::BN;
+  const int num_tiles = m_blocks * n_blocks;
+  const int num_kb = (K + G::BK - 1) / G::BK;
 
   if (warp == 0) {
     // ===== TMA producer (one per CTA): own A rows + own half of B; bytes are accounted on the leader's barrier =====

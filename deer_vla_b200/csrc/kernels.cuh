@@ -124,6 +124,8 @@ layernorm_warp_kernel(const TIn* in, int in_ld, LnMap in_map, const float* __res
                       int groups, TOut* out, int out_ld, LnMap map, TOut* out2, int out2_ld,
                       int relu, int rows_host, const int* __restrict__ n_dev, int n_mul) {
   constexpr int D = NVEC * 128;
+  pdl_wait();
+  pdl_trigger();
   const int rows = dyn_rows(rows_host, n_dev, n_mul);
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);

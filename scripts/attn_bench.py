@@ -34,4 +34,8 @@ lib.deer_attn_debug(1, buf.ctypes.data_as(C.c_void_p), buf.size)
 d = buf.reshape(512, 8)[:148, :8]
 tiles = 2 * (B * H) / 148
 m = d.mean(0) / tiles
-print("cycles per tile (softmax warp 2): wait_S %.0f | S loads issued->landed %.0f, max+exchange %.0f | epilogue: wait_O %.0f, rest %.0f | exp+P-store %.0f | total %.0f" % (m[0], m[6], m[1], m[5], m[2], m[3], d.sum(1).mean() / tiles))
+if os.environ.get("DEER_ATTN_V3") or os.environ.get("DEER_ATTN_V4"):
+    print("cycles per tile (softmax warp 2): wait_S %.0f | S loads issued->landed %.0f, max+exchange %.0f | epilogue: wait_O %.0f, rest %.0f | exp+P-store %.0f | total %.0f" % (m[0], m[6], m[1], m[5], m[2], m[3], d.sum(1).mean() / tiles))
+else:   # v5: warp 2 belongs to group 0 and sees every other tile
+    m = m * 2
+    print("v5 cycles per tile of ONE group (warp 2): wait_S %.0f | softmax (8 chunks) %.0f | wait_O %.0f | output %.0f | total %.0f  (two groups overlap: SM time per tile ~ total/2)" % (m[0], m[1], m[2], m[3], 2 * d.sum(1).mean() / tiles))

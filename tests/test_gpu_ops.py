@@ -109,6 +109,40 @@ def test_attention_hd64(impl, B, H, Sq, Sk):
     assert (out.float() - ref).abs().max().item() <= 2e-2
 
 
+@pytest.mark.parametrize("kind", ["peaked", "ramp", "late_spike", "tail_spike"])
+def test_attention_tc_large_logits(kind):
+    """The chunk-pipelined softmax of attn_tc_kernel takes probabilities relative to a running reference that is clamped to
+    (chunk max - 30k) at stage k instead of the full-row max.  Rows whose late keys beat the early ones by far more than 2^30
+    must still come out as the exact softmax (the stale mass is <= 2^-22 of the row)."""
+    from deer_vla_b200.engine import op_attention
+    B, H, S = 4, 4, 257
+    g = torch.Generator(device="cuda").manual_seed(11)
+    q = torch.randn(B, S, H, 64, device="cuda", generator=g)
+    k = torch.randn(B, S, H, 64, device="cuda", generator=g)
+    v = torch.randn(B, S, H, 64, device="cuda", generator=g).bfloat16()
+    if kind == "peaked":                 # logits ~ N(0, 36^2): nearly one-hot rows, winners anywhere
+        q, k = q * 6.0, k * 6.0
+    else:
+        u = torch.nn.functional.normalize(torch.randn(64, device="cuda", generator=g), dim=0)
+        q = q * 0.3 + 16.0 * u           # every query has a large component along u ...
+        pos = torch.arange(S, device="cuda", dtype=torch.float32)
+        if kind == "ramp":               # ... and key j's component along u grows with j: logit(j) ~ 2*16*j/S*12 -> +100 nats end to end
+            amp = 50.0 * pos / S
+        elif kind == "late_spike":       # one key in the last chunk of each half towers over everything before it
+            amp = torch.zeros(S, device="cuda")
+            amp[120], amp[250] = 40.0, 45.0
+        else:                            # the 257th key (handled on CUDA cores) is the winner
+            amp = torch.zeros(S, device="cuda")
+            amp[256] = 40.0
+        k = k * 0.3 + amp.view(1, S, 1, 1) * u
+    q, k = q.bfloat16(), k.bfloat16()
+    out = op_attention(q, k, v, 0.125, impl="tc")
+    torch.cuda.synchronize()
+    ref = _ref_attn(q, k, v, 0.125)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() <= 3e-2
+
+
 def test_attention_fp32_simt():
     from deer_vla_b200.engine import op_attention
     g = torch.Generator(device="cuda").manual_seed(3)
