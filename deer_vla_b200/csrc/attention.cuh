@@ -315,6 +315,8 @@ flash_attn_hd64_kernel(const bf16* __restrict__ Qg, int ldq, const bf16* __restr
   const bf16* V = Vg + static_cast<size_t>(b) * Sk * ldk + h * 64;
   bf16* O = Og + static_cast<size_t>(b) * Sq * ldo + h * 64;
 
+  pdl_wait();
+  pdl_trigger();
   flash_load_tile(sQ, Q, ldq, q0, Sq, tid);
   flash_load_tile(sK[0], K, ldk, 0, Sk, tid);
   flash_load_tile(sV[0], V, ldk, 0, Sk, tid);
@@ -460,6 +462,8 @@ template <int HD>
 __global__ void __launch_bounds__(64)
 attn_llm_mma_kernel(AttnParams p) {
   extern __shared__ __align__(128) uint8_t smraw[];
+  pdl_wait();
+  pdl_trigger();
   const int h = blockIdx.x, b = blockIdx.y;
   const int nb = p.n_dev ? min(*p.n_dev, p.B_host) : p.B_host;
   if (b >= nb) return;

@@ -235,9 +235,8 @@ static int run_attention(int impl, int dtype, const AttnParams& p, std::string* 
   if (done) {
   } else if ((impl == 0 || impl == 3) && plain) {
     dim3 grid((p.Sq + 63) / 64, p.H, p.B_host);
-    flash_attn_hd64_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const bf16*>(p.Q), p.ldq, reinterpret_cast<const bf16*>(p.K),
-                                                 reinterpret_cast<const bf16*>(p.V), p.ldk, reinterpret_cast<bf16*>(p.O), p.ldo, p.Sq, p.Sk,
-                                                 p.scale * 1.4426950408889634f);
+    launch_k(flash_attn_hd64_kernel, grid, dim3(128), 0, st, pdl, reinterpret_cast<const bf16*>(p.Q), p.ldq, reinterpret_cast<const bf16*>(p.K),
+             reinterpret_cast<const bf16*>(p.V), p.ldk, reinterpret_cast<bf16*>(p.O), p.ldo, p.Sq, p.Sk, p.scale * 1.4426950408889634f);
   } else if ((impl == 2 || impl == 4) && dtype == 0 && p.Sq <= 32 && p.Sk <= 128 && (p.hd == 64 || p.hd == 128) && (p.ldq % 8) == 0 &&
              (p.ldk % 8) == 0 && (p.ldv % 8) == 0 && (p.ldo % 2) == 0 && ((reinterpret_cast<uintptr_t>(p.Q) | reinterpret_cast<uintptr_t>(p.K) |
              reinterpret_cast<uintptr_t>(p.V)) & 15) == 0 && (impl == 4 || getenv("DEER_ATTN_LLM_SIMT") == nullptr)) {
@@ -249,8 +248,8 @@ static int run_attention(int impl, int dtype, const AttnParams& p, std::string* 
     }
     dim3 grid(p.H, p.B_host);
     const size_t sm = attn_llm_mma_smem(p.Sk, p.hd);
-    if (p.hd == 64) attn_llm_mma_kernel<64><<<grid, 64, sm, st>>>(p);
-    else attn_llm_mma_kernel<128><<<grid, 64, sm, st>>>(p);
+    if (p.hd == 64) launch_k(attn_llm_mma_kernel<64>, grid, dim3(64), sm, st, pdl, p);
+    else launch_k(attn_llm_mma_kernel<128>, grid, dim3(64), sm, st, pdl, p);
   } else if ((impl == 2 || impl == 4) && attn_small_smem(p.Sq, p.Sk, p.hd) <= 200 * 1024) {
     static bool attr_done = false;
     if (!attr_done) {
@@ -967,7 +966,7 @@ template <typename T> struct StepImpl {
       AttnParams a{};
       a.Q = c->p_q; a.K = c->p_kv; a.V = tp(c->p_kv) + inner; a.O = c->p_att;
       a.ldq = inner; a.ldk = a.ldv = 2 * inner; a.ldo = inner; a.Sq = nl; a.Sk = kvr; a.H = f.perc_heads; a.hd = 64; a.scale = 0.125f; a.B_host = NI;
-      RET(run_attention(0, c->dtype, a, &c->err, &c->stats, st));
+      RET(run_attention(0, c->dtype, a, &c->err, &c->stats, st, c->gemm.pdl));
       RET(gemm(c->p_att, inner, NImax * nl, w.w_out, inner, NI * nl, Wd, inner, c->lat, Wd, 1, nullptr, ACT_NONE, nullptr, c->lat, Wd, nullptr, 0));
       RET(ln<float, T>(c->lat, Wd, w.ff_g, w.ff_b, 1, Wd, tp(c->p_latn), Wd, id, nullptr, 0, 0, NI * nl, nullptr, 0));
       const int ffd = f.perc_ff_mult * Wd;
@@ -1001,7 +1000,7 @@ template <typename T> struct StepImpl {
       a.Q = c->l_q; a.K = c->l_kv; a.V = tp(c->l_kv) + xin; a.O = c->l_att;
       a.ldq = xin; a.ldk = a.ldv = 2 * xin; a.ldo = xin; a.Sq = S; a.Sk = nl2; a.H = f.xattn_heads; a.hd = 64; a.scale = 0.125f;
       a.qmode = c->meta[cur].xmode; a.B_host = n; a.n_dev = nd;
-      RET(run_attention(2, c->dtype, a, &c->err, &c->stats, st));
+      RET(run_attention(2, c->dtype, a, &c->err, &c->stats, st, c->gemm.pdl));
       RET(gemm(c->l_att, xin, Mmax, w.xw_out, xin, M, D, xin, x, D, 1, nullptr, ACT_NONE, w.attn_gate_tanh, x, D, nd, S));
       RET(ln<float, T>(x, D, w.xff_g, w.xff_b, 1, D, tp(c->l_ln), D, id, nullptr, 0, 0, M, nd, S));
       const int ffd = f.xattn_ff_mult * D;
@@ -1019,7 +1018,7 @@ template <typename T> struct StepImpl {
     a.Q = c->l_qkv; a.K = tp(c->l_qkv) + D; a.V = tp(c->l_qkv) + 2 * D; a.O = c->l_att;
     a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D; a.Sq = a.Sk = S; a.H = f.n_heads; a.hd = c->hd; a.scale = 1.0f / std::sqrt((float)c->hd);
     a.causal = 1; a.alibi_slopes = c->alibi; a.kv_len = c->meta[cur].valid_len; a.B_host = n; a.n_dev = nd;
-    RET(run_attention(2, c->dtype, a, &c->err, &c->stats, st));
+    RET(run_attention(2, c->dtype, a, &c->err, &c->stats, st, c->gemm.pdl));
     RET(gemm(c->l_att, D, Mmax, w.w_out, D, M, D, D, x, D, 1, nullptr, ACT_NONE, nullptr, x, D, nd, S));
     RET(ln<float, T>(x, D, w.ln2_g, nullptr, 1, D, tp(c->l_ln), D, id, nullptr, 0, 0, M, nd, S));
     const int ffd = f.mlp_ratio * D;
@@ -1039,9 +1038,9 @@ template <typename T> struct StepImpl {
     const int D = f.d_model, H = f.lstm_hidden, LL = f.lstm_layers, Bm = f.max_batch, d0 = f.mlp_dim0, d1 = f.mlp_dim1;
     const int* nd = nact();
     const EpisodeMeta& m = c->meta[cur];
-    maxpool_kernel<T><<<dim3((D + 255) / 256, n), 256, 0, st>>>(c->x[cur], m.valid_len, tp(c->a0), D + H, f.debug_taps ? c->tap_pooled : nullptr, S, D, n, nd);
+    launch_k(maxpool_kernel<T>, dim3((D + 255) / 256, n), dim3(256), 0, st, c->gemm.pdl, c->x[cur], m.valid_len, tp(c->a0), D + H, f.debug_taps ? c->tap_pooled : nullptr, S, D, n, nd);
     KLAUNCH_CHECK("maxpool");
-    lstm_gather_h_kernel<T><<<dim3(n, LL), 256, 0, st>>>(c->h_state, m.slot, tp(c->a0), D + H, D, tp(c->a_rest), 2 * H, LL, H, Bm, n, nd);
+    launch_k(lstm_gather_h_kernel<T>, dim3(n, LL), dim3(256), 0, st, c->gemm.pdl, c->h_state, m.slot, tp(c->a0), D + H, D, tp(c->a_rest), 2 * H, LL, H, Bm, n, nd);
     KLAUNCH_CHECK("lstm_gather_h");
     for (int l = 0; l < LL; ++l) {
       const LstmLayerW& w = c->lstm[l];
@@ -1050,7 +1049,7 @@ template <typename T> struct StepImpl {
       RET(gemm(A, K, Bm, w.w_cat, K, n, 4 * H, K, c->gates, 4 * H, 1, w.b_sum, ACT_NONE, nullptr, nullptr, 0, nd, 1));
       T* y = (l + 1 < LL) ? tp(c->a_rest) + (size_t)l * Bm * 2 * H : tp(c->head_in);
       const int y_ld = (l + 1 < LL) ? 2 * H : H;
-      lstm_cell_kernel<T><<<n, 256, 0, st>>>(c->gates, c->c_state, m.slot, l, LL, c->cand_h, c->cand_c, w.ln_g, w.ln_b, y, y_ld, H, Bm, n, nd);
+      launch_k(lstm_cell_kernel<T>, dim3(n), dim3(256), 0, st, c->gemm.pdl, c->gates, c->c_state, m.slot, l, LL, c->cand_h, c->cand_c, w.ln_g, w.ln_b, y, y_ld, H, Bm, n, nd);
       KLAUNCH_CHECK("lstm_cell");
     }
     // both MLP heads: [Linear, LN, ReLU] x2 fused across heads, then the tiny output layers
@@ -1059,7 +1058,7 @@ template <typename T> struct StepImpl {
     RET(gemm(c->y1, 2 * d0, Bm, c->w_mlp2_pose, d0, n, d1, d0, c->mlp2, 2 * d1, 1, c->b_mlp2, ACT_NONE, nullptr, nullptr, 0, nd, 1));
     RET(gemm(tp(c->y1) + d0, 2 * d0, Bm, c->w_mlp2_grip, d0, n, d1, d0, c->mlp2 + d1, 2 * d1, 1, c->b_mlp2 + d1, ACT_NONE, nullptr, nullptr, 0, nd, 1));
     RET(ln<float, float>(c->mlp2, d1, c->g_mlp2, c->be_mlp2, 2, d1, c->y2, d1, LnMap{0, 0, 0}, nullptr, 0, 1, 2 * n, nd, 2));
-    head_out_kernel<<<n, 256, 0, st>>>(c->y2, d1, c->w3_pose, c->b3_pose, c->w3_grip, c->b3_grip, c->cur_pose, c->cur_grip, n, nd);
+    launch_k(head_out_kernel, dim3(n), dim3(256), 0, st, c->gemm.pdl, c->y2, d1, c->w3_pose, c->b3_pose, c->w3_grip, c->b3_grip, c->cur_pose, c->cur_grip, n, nd);
     KLAUNCH_CHECK("head_out");
     return DEER_OK;
   }

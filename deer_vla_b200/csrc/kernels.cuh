@@ -268,6 +268,8 @@ __global__ void embed_kernel(const int64_t* __restrict__ ids, const T* __restric
 template <typename T>
 __global__ void maxpool_kernel(const float* __restrict__ x, const int* __restrict__ valid_len, T* __restrict__ out, int out_ld,
                                float* __restrict__ out_f32, int S, int D, int n_host, const int* __restrict__ n_dev) {
+  pdl_wait();
+  pdl_trigger();
   const int n = dyn_rows(n_host, n_dev, 1);
   const int r = blockIdx.y;
   if (r >= n) return;
@@ -287,6 +289,8 @@ __global__ void maxpool_kernel(const float* __restrict__ x, const int* __restric
 template <typename T>
 __global__ void lstm_gather_h_kernel(const float* __restrict__ h_state, const int* __restrict__ slot, T* __restrict__ a0, int ld0, int off0,
                                      T* __restrict__ a_rest, int ld_rest, int layers, int Hh, int nstride, int n_host, const int* __restrict__ n_dev) {
+  pdl_wait();
+  pdl_trigger();
   const int n = dyn_rows(n_host, n_dev, 1);
   const int r = blockIdx.x, l = blockIdx.y;
   if (r >= n) return;
@@ -303,6 +307,8 @@ lstm_cell_kernel(const float* __restrict__ gates, const float* __restrict__ c_st
                  float* __restrict__ cand_h, float* __restrict__ cand_c, const float* __restrict__ gamma, const float* __restrict__ beta,
                  T* __restrict__ y, int y_ld, int Hh, int nstride, int n_host, const int* __restrict__ n_dev) {
   __shared__ float red[32];
+  pdl_wait();
+  pdl_trigger();
   const int n = dyn_rows(n_host, n_dev, 1);
   const int r = blockIdx.x;
   if (r >= n) return;
@@ -346,6 +352,8 @@ __global__ void __launch_bounds__(256)
 head_out_kernel(const float* __restrict__ y2, int d1, const float* __restrict__ w_pose, const float* __restrict__ b_pose,
                 const float* __restrict__ w_grip, const float* __restrict__ b_grip, float* __restrict__ pose, float* __restrict__ grip,
                 int n_host, const int* __restrict__ n_dev) {
+  pdl_wait();
+  pdl_trigger();
   const int n = dyn_rows(n_host, n_dev, 1);
   const int r = blockIdx.x;
   if (r >= n) return;
