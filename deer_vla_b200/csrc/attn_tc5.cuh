@@ -119,38 +119,54 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: QK(n+1) is issued before PV(n), so each group finds its next scores ready =====
+    // ===== MMA issuer.  The two softmax groups are independent, so the issuer must not make one wait for the other: QK(nq) and
+    // PV(np) are issued in whichever order their preconditions come true (a fixed QK(n+1)-then-PV(n) order left the group that
+    // had finished its probabilities waiting until the OTHER group had drained its previous tile). =====
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16_major(128, A::NMMA, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16_major(128, 64, 0, 1);     // B = V, MN-major
-      auto issue_qk = [&](int n) {
-        const int is = n / n_sub, t = n % n_sub, kb = is & 1, qb = n & 1, u = n & 1;
-        if (t == 0) mbar_wait(&kv_full[kb], (is >> 1) & 1);
-        mbar_wait(&q_full[qb], (n >> 1) & 1);
-        if (n >= 2) mbar_wait(&o_empty[u], ((n >> 1) - 1) & 1);        // the group has drained its previous tile
-        tc_fence_after();
-        const uint32_t q_addr = smem_u32(smem + A5::OFF_Q + qb * A::Q_BYTES);
-        const uint32_t k_addr = smem_u32(smem + A5::OFF_K + kb * A::KV_BYTES);
+      int nq = 0, np = 0;                                  // next QK / next PV to issue
+      uint32_t idle = 0;
+      while (np < total) {
+        bool did = false;
+        if (nq < total && nq < np + 2) {                   // at most two tiles in flight (two TMEM buffers)
+          const int is = nq / n_sub, t = nq - is * n_sub, kb = is & 1, qb = nq & 1, u = nq & 1;
+          const bool ok = (t != 0 || mbar_test(&kv_full[kb], (is >> 1) & 1)) && mbar_test(&q_full[qb], (nq >> 1) & 1) &&
+                          (nq < 2 || mbar_test(&o_empty[u], ((nq >> 1) - 1) & 1));       // the group has drained its previous tile
+          if (ok) {
+            tc_fence_after();
+            const uint32_t q_addr = smem_u32(smem + A5::OFF_Q + qb * A::Q_BYTES);
+            const uint32_t k_addr = smem_u32(smem + A5::OFF_K + kb * A::KV_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + static_cast<uint32_t>(256 * u), make_desc_sw128(q_addr) + static_cast<uint64_t>(2 * k),
-                    make_desc_sw128(k_addr) + static_cast<uint64_t>(2 * k), idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(&s_full[u]);
-        umma_commit(&q_empty[qb]);
-      };
-      if (total > 0) issue_qk(0);
-      for (int n = 0; n < total; ++n) {
-        if (n + 1 < total) issue_qk(n + 1);
-        const int is = n / n_sub, t = n % n_sub, kb = is & 1, u = n & 1;
-        mbar_wait(&p_full[u], (n >> 1) & 1);
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(smem + A5::OFF_V + kb * A::KV_BYTES);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + static_cast<uint32_t>(256 * u), make_desc_sw128(q_addr) + static_cast<uint64_t>(2 * k),
+                        make_desc_sw128(k_addr) + static_cast<uint64_t>(2 * k), idesc_s, k != 0 ? 1u : 0u);
+            umma_commit(&s_full[u]);
+            umma_commit(&q_empty[qb]);
+            ++nq;
+            did = true;
+          }
+        }
+        if (np < nq) {
+          const int is = np / n_sub, t = np - is * n_sub, kb = is & 1, u = np & 1;
+          if (mbar_test(&p_full[u], (np >> 1) & 1)) {
+            tc_fence_after();
+            const uint32_t v_addr = smem_u32(smem + A5::OFF_V + kb * A::KV_BYTES);
 #pragma unroll 1
-        for (int k = 0; k < pv_steps; ++k)
-          umma_bf16_ts(tmem_base + static_cast<uint32_t>(256 * u + 128), tmem_base + static_cast<uint32_t>(256 * u + 8 * k),
-                       make_desc(v_addr + static_cast<uint32_t>(k) * 2048u, 1024u, 1024u), idesc_pv, k != 0 ? 1u : 0u);
-        umma_commit(&o_full[u]);
-        if (t == n_sub - 1) umma_commit(&kv_empty[kb]);
+            for (int k = 0; k < pv_steps; ++k)
+              umma_bf16_ts(tmem_base + static_cast<uint32_t>(256 * u + 128), tmem_base + static_cast<uint32_t>(256 * u + 8 * k),
+                           make_desc(v_addr + static_cast<uint32_t>(k) * 2048u, 1024u, 1024u), idesc_pv, k != 0 ? 1u : 0u);
+            umma_commit(&o_full[u]);
+            if (t == n_sub - 1) umma_commit(&kv_empty[kb]);
+            ++np;
+            did = true;
+          }
+        }
+        if (did) idle = 0;
+        else {
+          __nanosleep(32);
+          if (++idle > (1u << 26)) __trap();               // a protocol bug must surface as a launch failure, never as a hung GPU
+        }
       }
     }
   } else if (warp < 10) {
@@ -238,23 +254,17 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }                                                                                                      \
         tmem_st_32x32b_x16(tbuf + static_cast<uint32_t>(16 * (K)), pk);                                        \
       }
-      // chunk k+1 is requested before chunk k is processed; P chunk k lands on score columns [16k, 16k+16), all inside chunks <= k
-      tmem_ld_wait(); tmem_ld_32x32(tbuf + 32u, sb);
-      STAGE5(sa, 0)
-      tmem_ld_wait(); tmem_ld_32x32(tbuf + 64u, sa);
-      STAGE5(sb, 1)
-      tmem_ld_wait(); tmem_ld_32x32(tbuf + 96u, sb);
-      STAGE5(sa, 2)
-      tmem_ld_wait(); tmem_ld_32x32(tbuf + 128u, sa);
-      STAGE5(sb, 3)
-      tmem_ld_wait(); tmem_ld_32x32(tbuf + 160u, sb);
-      STAGE5(sa, 4)
-      tmem_ld_wait(); tmem_ld_32x32(tbuf + 192u, sa);
-      STAGE5(sb, 5)
-      tmem_ld_wait(); tmem_ld_32x32(tbuf + 224u, sb);
-      STAGE5(sa, 6)
-      tmem_ld_wait();
-      STAGE5(sb, 7)
+      // chunk k+1 is requested before chunk k is processed; P chunk k lands on score columns [16k, 16k+16), all inside chunks <= k.
+      // Rolled (two stages per iteration, one per ping-pong buffer): the fully unrolled body did not fit the instruction cache
+      // (ncu: 19 % of the warp stall samples were "no instruction").
+#pragma unroll 1
+      for (int kk = 0; kk < 4; ++kk) {
+        tmem_ld_wait(); tmem_ld_32x32(tbuf + static_cast<uint32_t>(64 * kk + 32), sb);
+        STAGE5(sa, 2 * kk)
+        tmem_ld_wait();
+        if (kk < 3) tmem_ld_32x32(tbuf + static_cast<uint32_t>(64 * kk + 64), sa);
+        STAGE5(sb, 2 * kk + 1)
+      }
 #undef STAGE5
       float l = (l0 + l1) + (l2 + l3);
 #pragma unroll 1
@@ -276,32 +286,40 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(&o_full[u], par);
       tc_fence_after();
       TICK5(2);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {                        // 16 O columns at a time
-        float v[16];
-        tmem_ld_32x32_x16(tbuf + static_cast<uint32_t>(128 + c * 16), v);
+      {
+        float va[32], vb[32];                              // the whole 64-column O row, both loads in flight together
+        tmem_ld_32x32(tbuf + 128u, va);
+        tmem_ld_32x32(tbuf + 160u, vb);
         tmem_ld_wait();
         for (int j = 0; j < n_tail; ++j) {
           const int kr = A::NMMA + j;
           const float pj = xtail[j * 128 + rloc];
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {                 // two 16-byte chunks = 16 d; every lane reads the same address (broadcast)
-            const uint4 y = *reinterpret_cast<const uint4*>(sv + kr * 128 + (((c * 2 + cc) ^ (kr & 7)) << 4));
+          for (int cc = 0; cc < 8; ++cc) {                 // eight 16-byte chunks = 64 d; every lane reads the same address (broadcast)
+            const uint4 y = *reinterpret_cast<const uint4*>(sv + kr * 128 + ((cc ^ (kr & 7)) << 4));
             const __nv_bfloat162* y2 = reinterpret_cast<const __nv_bfloat162*>(&y);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 f = __bfloat1622float2(y2[e]);
-              v[cc * 8 + 2 * e] = fmaf(pj, f.x, v[cc * 8 + 2 * e]);
-              v[cc * 8 + 2 * e + 1] = fmaf(pj, f.y, v[cc * 8 + 2 * e + 1]);
+              if (cc < 4) {
+                va[cc * 8 + 2 * e] = fmaf(pj, f.x, va[cc * 8 + 2 * e]);
+                va[cc * 8 + 2 * e + 1] = fmaf(pj, f.y, va[cc * 8 + 2 * e + 1]);
+              } else {
+                vb[(cc - 4) * 8 + 2 * e] = fmaf(pj, f.x, vb[(cc - 4) * 8 + 2 * e]);
+                vb[(cc - 4) * 8 + 2 * e + 1] = fmaf(pj, f.y, vb[(cc - 4) * 8 + 2 * e + 1]);
+              }
             }
           }
         }
 #pragma unroll
-        for (int j = 0; j < 16; j += 8) {
+        for (int j = 0; j < 32; j += 8) {
           uint4 o;
-          o.x = pack_bf16x2(v[j] * inv, v[j + 1] * inv); o.y = pack_bf16x2(v[j + 2] * inv, v[j + 3] * inv);
-          o.z = pack_bf16x2(v[j + 4] * inv, v[j + 5] * inv); o.w = pack_bf16x2(v[j + 6] * inv, v[j + 7] * inv);
-          *reinterpret_cast<uint4*>(ost + lane * A5::OST_ROW + c * 32 + j * 2) = o;
+          o.x = pack_bf16x2(va[j] * inv, va[j + 1] * inv); o.y = pack_bf16x2(va[j + 2] * inv, va[j + 3] * inv);
+          o.z = pack_bf16x2(va[j + 4] * inv, va[j + 5] * inv); o.w = pack_bf16x2(va[j + 6] * inv, va[j + 7] * inv);
+          *reinterpret_cast<uint4*>(ost + lane * A5::OST_ROW + j * 2) = o;
+          o.x = pack_bf16x2(vb[j] * inv, vb[j + 1] * inv); o.y = pack_bf16x2(vb[j + 2] * inv, vb[j + 3] * inv);
+          o.z = pack_bf16x2(vb[j + 4] * inv, vb[j + 5] * inv); o.w = pack_bf16x2(vb[j + 6] * inv, vb[j + 7] * inv);
+          *reinterpret_cast<uint4*>(ost + lane * A5::OST_ROW + 64 + j * 2) = o;
         }
       }
       tc_fence_before();
