@@ -1092,7 +1092,8 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
     cudaEventRecord(c->ev_step0, s.st);
   }
   c->gemm.tag = 0;
-  c->gemm.pdl = (c->cap_level < 0) && !c->gemm.profile;
+  static const bool pdl_in_graph = getenv("DEER_PDL_GRAPH") ? atoi(getenv("DEER_PDL_GRAPH")) != 0 : true;   // programmatic edges inside the captured graph (B=1: 3.03 -> 2.89 ms)
+  c->gemm.pdl = (c->cap_level < 0 || pdl_in_graph) && !c->gemm.profile;
   RET(s.vision(rgb, grip));
   c->gemm.tag = 2;
   if (c->dtype == 1) embed_kernel<float><<<n * S, 256, 0, s.st>>>(ids, reinterpret_cast<const float*>(c->wte), c->x[0], n * S, f.d_model, f.vocab);
@@ -1380,6 +1381,12 @@ extern "C" int deer_get_tap(deer_ctx* c, const char* name, int layer, float* out
   CK(cudaMemcpy(out, src, numel * 4, cudaMemcpyDeviceToHost));
   for (int i = 0; i < 4; ++i) shape_out[i] = sh[i];
   return DEER_OK;
+}
+
+extern "C" int deer_set_launch_overlap(int enable) {
+  const int prev = g_pdl_env ? 1 : 0;
+  g_pdl_env = enable != 0;
+  return prev;
 }
 
 extern "C" int deer_set_profile(deer_ctx* c, int enable) {

@@ -100,6 +100,11 @@ class DeerEngine:
         self._check(self.lib.deer_get_stats(self._h, C.byref(s)))
         return s
 
+    @staticmethod
+    def set_launch_overlap(enable: bool) -> bool:
+        """Process-wide switch of programmatic dependent launch (see include/deer_engine.h); returns the previous setting."""
+        return bool(_lib.load().deer_set_launch_overlap(int(enable)))
+
     def set_profile(self, enable: bool):
         self._check(self.lib.deer_set_profile(self._h, int(enable)))
 

@@ -172,6 +172,12 @@ typedef struct deer_profile {
 int deer_set_profile(deer_ctx* ctx, int enable);
 int deer_get_profile(deer_ctx* ctx, deer_profile* out);
 
+/* Launch overlap (process-wide): 1 (default) launches the per-layer kernels with programmatic stream serialization, so a
+ * kernel's prologue overlaps its predecessor's tail (the reference's eager PyTorch path serialises ~600 launches per step,
+ * eval_utils.py:433); 0 = plain stream order.  Results are bit-identical either way (tested); returns the previous setting.
+ * Environment DEER_PDL=0/1 sets the initial value. */
+int deer_set_launch_overlap(int enable);
+
 /* One frame of the threshold-calibration pass in the reference's TRAINING layout -- replaces generate_action_values
  * (value_net.py:300-399): MPTFlamingo.forward(return_in_feat, only_extra_exit) over windows of frames (flamingo_mpt.py:476-492)
  * followed by ActionValueNet.forward(mode='generate') (value_net.py:134-160).  Call it for frames t = 0 .. window-2 of n
