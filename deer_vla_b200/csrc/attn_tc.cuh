@@ -141,13 +141,6 @@ __device__ __forceinline__ void tmem_ld_32x32_x16(uint32_t taddr, float (&v)[16]
                : "r"(taddr) : "memory");
 }
 
-// one MUFU.EX2, no range fix-up (arguments are <= 0 here: s*scale - max*scale; exp2(-inf) = 0)
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 // A/B switches of the attention kernel's barrier flavour (see scripts/gpu_exp3.sh)
 #ifdef DEER_ATTN_RELAXED
 #define ATT_ARRIVE(bar) mbar_arrive_relaxed(bar)

@@ -38,17 +38,30 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.0f);
   return v;
 }
-// Fast forms for the tensor-core epilogue (results are rounded to bf16 or added to an O(1) fp32 residual):
-// erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7) with __expf / fast reciprocal; QuickGELU with fast divide.
+// Fast forms for the tensor-core epilogue (results are rounded to bf16 or added to an O(1) fp32 residual).
+// one MUFU.EX2, no range fix-up
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Exact (erf) GELU with ONE MUFU op and no reciprocal: gelu(x) = x * Phi(x) with Phi(-a) = 0.5 * erfc(a / sqrt 2) = 2^L(a).
+// L is a degree-7 polynomial fitted on [0, 6] (max |dL| 5.7e-6, L(0) = -1 exactly; beyond 6, Phi(-a) < 1e-9 is clamped):
+//   x < 0: x * 2^L(|x|)        x >= 0: x - x * 2^L(x)
+// so the negative tail keeps RELATIVE accuracy (no 1 - erf cancellation).  |err| <= 7e-7 absolute in fp32 over [-8, 8]
+// (fit + error check: DESIGN.md section 4); the previous Abramowitz-Stegun 7.1.26 form needed a reciprocal and an exp.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * __expf(-z * z);           // erf(|x|/sqrt2)
-  return 0.5f * x * (1.0f + copysignf(e, x));
+  const float a = fminf(fabsf(x), 6.0f);
+  float p = -1.793804472e-06f;
+  p = fmaf(p, a, 6.072663382e-05f);
+  p = fmaf(p, a, -9.231893346e-04f);
+  p = fmaf(p, a, 8.476860821e-03f);
+  p = fmaf(p, a, -5.389096215e-02f);
+  p = fmaf(p, a, -4.585415721e-01f);
+  p = fmaf(p, a, -1.151214361e+00f);
+  p = fmaf(p, a, -1.0f);
+  const float xt = x * ex2_approx(p);
+  return x >= 0.0f ? x - xt : xt;
 }
 // x*sigmoid(1.702x) with sigmoid(y) = 0.5 + 0.5*tanh(y/2): ONE MUFU op per element (tanh.approx.f32, rel. err 2^-11,
 // i.e. <= 2.5e-4*|x| absolute -- an order of magnitude below the bf16 rounding of the stored value)

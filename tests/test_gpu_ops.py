@@ -66,6 +66,28 @@ def test_gemm_epilogues(impl, act, M):
     assert (out - ref).abs().max().item() <= 2e-3
 
 
+@pytest.mark.parametrize("M", [640, 9000])            # 1-CTA and 2-CTA tcgen05 kernels
+def test_gemm_epilogue_gelu_is_exact_erf_gelu(M):
+    """The tensor-core epilogue's GELU is nn.GELU() (erf form, the reference's FeedForward / MPT MLP activation) to fp32
+    accuracy, not the tanh approximation: identity weights feed bf16-exact pre-activations on [-9, 9] (dense around 0 and in
+    the negative tail, where 1 + erf cancels) through the epilogue with fp32 output; |err| <= 2e-6 against float64."""
+    from deer_vla_b200.engine import op_gemm
+    K = N = 256
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.cat([torch.linspace(-9, 9, M * N // 2, device="cuda"), torch.randn(M * N - M * N // 2, device="cuda", generator=g) * 2.0])
+    x = x[torch.randperm(M * N, device="cuda", generator=g)].view(M, N).bfloat16()
+    W = torch.eye(N, K, device="cuda").bfloat16()
+    out = op_gemm(x.contiguous(), W, act=1, resid=torch.zeros(M, N, device="cuda"), impl="tcgen05")
+    torch.cuda.synchronize()
+    xd = x.double()
+    ref = 0.5 * xd * (1.0 + torch.erf(xd / math.sqrt(2.0)))
+    err = (out.double() - ref).abs()
+    assert err.max().item() <= 2e-6, (err.max().item(), xd.flatten()[err.argmax()].item())
+    tail = (xd < -3.0) & (xd > -6.0)                    # relative accuracy where the value itself is 4e-3 .. 6e-9 (beyond -6 it is clamped)
+    rel = (err[tail] / ref[tail].abs().clamp_min(1e-12)).max().item()
+    assert rel <= 1e-3, rel
+
+
 @pytest.mark.parametrize("impl", ["simt", "tcgen05"])
 def test_gemm_dynamic_m_and_strides(impl):
     from deer_vla_b200.engine import op_gemm
@@ -111,9 +133,10 @@ def test_attention_hd64(impl, B, H, Sq, Sk):
 
 @pytest.mark.parametrize("kind", ["peaked", "ramp", "late_spike", "tail_spike"])
 def test_attention_tc_large_logits(kind):
-    """The chunk-pipelined softmax of attn_tc_kernel takes probabilities relative to a running reference that is clamped to
-    (chunk max - 30k) at stage k instead of the full-row max.  Rows whose late keys beat the early ones by far more than 2^30
-    must still come out as the exact softmax (the stale mass is <= 2^-22 of the row)."""
+    """The chunk-pipelined softmax of the tcgen05 attention kernels takes probabilities relative to a running reference instead
+    of the full-row max (v5: the reference moves, with an exact power-of-two rescale of what is already stored, only when a chunk
+    max exceeds it by 2^60; v4: clamped to chunk max - 30k at stage k).  Rows whose late keys beat the early ones by far more
+    than that must still come out as the exact softmax."""
     from deer_vla_b200.engine import op_attention
     B, H, S = 4, 4, 257
     g = torch.Generator(device="cuda").manual_seed(11)
