@@ -229,12 +229,17 @@ def engine_arm(a):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     exit_hist = np.zeros(cfg.n_layers, dtype=np.int64)
     outs = []
+    ncu_range = os.environ.get("DEER_NCU_RANGE") is not None     # `ncu --profile-from-start off`: capture exactly the timed steps
+    if ncu_range:
+        torch.cuda.profiler.start()
     e0.record()
     for t in range(a.steps):
         r, g = frames[(a.warmup + t) % NF]
         outs.append(eng.step(r, g, ids, mask, slots, want_delta=False))
     e1.record()
     barrier()
+    if ncu_range:
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.stats().kernel_launches_total - launches0
