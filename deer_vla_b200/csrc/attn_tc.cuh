@@ -141,18 +141,6 @@ __device__ __forceinline__ void tmem_ld_32x32_x16(uint32_t taddr, float (&v)[16]
                : "r"(taddr) : "memory");
 }
 
-// A/B switches of the attention kernel's barrier flavour (see scripts/gpu_exp3.sh)
-#ifdef DEER_ATTN_RELAXED
-#define ATT_ARRIVE(bar) mbar_arrive_relaxed(bar)
-#else
-#define ATT_ARRIVE(bar) mbar_arrive(bar)
-#endif
-#ifdef DEER_ATTN_SPIN
-#define ATT_WAIT(bar, ph) mbar_wait_spin(bar, ph)
-#else
-#define ATT_WAIT(bar, ph) mbar_wait(bar, ph)
-#endif
-
 struct AttnTc {
   static constexpr int SKP = 272;                        // rows staged per K / V buffer (17 x 16)
   static constexpr int NMMA = 256;                       // keys that go through the tensor core
@@ -252,7 +240,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int it = blockIdx.x + is * gridDim.x;
         const int b = it / H, h = it % H;
         const int kb = is & 1;
-        ATT_WAIT(&kv_empty[kb], ((is >> 1) & 1) ^ 1u);
+        mbar_wait(&kv_empty[kb], ((is >> 1) & 1) ^ 1u);
         mbar_arrive_expect_tx(&kv_full[kb], 2 * A::KV_BYTES);
         uint8_t* sk = smem + A::OFF_K + kb * A::KV_BYTES;
         uint8_t* sv = smem + A::OFF_V + kb * A::KV_BYTES;
@@ -262,7 +250,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tma_load_2d(sv + A::HALF_BYTES, &tmV, &kv_full[kb], h * 64, b * Sk + A::HALF_ROWS);
         for (int t = 0; t < n_sub; ++t) {
           const int n = is * n_sub + t, qb = n & 1;
-          ATT_WAIT(&q_empty[qb], ((n >> 1) & 1) ^ 1u);
+          mbar_wait(&q_empty[qb], ((n >> 1) & 1) ^ 1u);
           mbar_arrive_expect_tx(&q_full[qb], A::Q_BYTES);
           tma_load_2d(smem + A::OFF_Q + qb * A::Q_BYTES, &tmQ, &q_full[qb], h * 64, b * Sq + t * 128);
         }
@@ -275,9 +263,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       constexpr uint32_t idesc_pv = make_idesc_bf16_major(128, 64, 0, 1);     // B = V, MN-major
       auto issue_qk = [&](int n) {
         const int is = n / n_sub, t = n % n_sub, kb = is & 1, qb = n & 1, u = n & 1;
-        if (t == 0) ATT_WAIT(&kv_full[kb], (is >> 1) & 1);
-        ATT_WAIT(&q_full[qb], (n >> 1) & 1);
-        if (n >= 2) ATT_WAIT(&o_empty[u], ((n >> 1) - 1) & 1);        // the buffer's previous tile has been drained
+        if (t == 0) mbar_wait(&kv_full[kb], (is >> 1) & 1);
+        mbar_wait(&q_full[qb], (n >> 1) & 1);
+        if (n >= 2) mbar_wait(&o_empty[u], ((n >> 1) - 1) & 1);        // the buffer's previous tile has been drained
         tc_fence_after();
         const uint32_t q_addr = smem_u32(smem + A::OFF_Q + qb * A::Q_BYTES);
         const uint32_t k_addr = smem_u32(smem + A::OFF_K + kb * A::KV_BYTES);
@@ -292,7 +280,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int n = 0; n < total; ++n) {
         if (n + 1 < total) issue_qk(n + 1);
         const int is = n / n_sub, t = n % n_sub, kb = is & 1, u = n & 1;
-        ATT_WAIT(&p_full[u], (n >> 1) & 1);
+        mbar_wait(&p_full[u], (n >> 1) & 1);
         tc_fence_after();
         const uint32_t v_addr = smem_u32(smem + A::OFF_V + kb * A::KV_BYTES);
 #pragma unroll 1
@@ -327,7 +315,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int is = n / n_sub, t = n % n_sub, kb = is & 1, u = n & 1;
       const int it = blockIdx.x + is * gridDim.x;
       const int b = it / H, h = it % H;
-      ATT_WAIT(&o_full[u], (n >> 1) & 1);
+      mbar_wait(&o_full[u], (n >> 1) & 1);
       tc_fence_after();
       TICK(5);
       const float inv = 1.0f / (xsum[(u * 2 + 0) * 128 + rloc] + xsum[(u * 2 + 1) * 128 + rloc]);
@@ -378,8 +366,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        ATT_ARRIVE(&o_empty[u]);
-        if (t == n_sub - 1) ATT_ARRIVE(&kv_empty[kb]);
+        mbar_arrive(&o_empty[u]);
+        if (t == n_sub - 1) mbar_arrive(&kv_empty[kb]);
       }
     };
 
@@ -392,7 +380,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         break;
       }
       const int is = n / n_sub, kb = is & 1, qb = n & 1, u = n & 1;
-      ATT_WAIT(&s_full[u], (n >> 1) & 1);
+      mbar_wait(&s_full[u], (n >> 1) & 1);
       tc_fence_after();
       TICK(0);
       if (VER == 4) {
@@ -420,7 +408,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             m = fmaxf(m, sj);
           }
           __syncwarp();
-          if (lane == 0) ATT_ARRIVE(&q_empty[qb]);
+          if (lane == 0) mbar_arrive(&q_empty[qb]);
         }
         tmem_ld_wait();
         tmem_ld_32x32(ts + 32u, sb);
@@ -485,7 +473,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) ATT_ARRIVE(&p_full[u]);
+        if (lane == 0) mbar_arrive(&p_full[u]);
         TICK(3);
         continue;
       }
@@ -508,7 +496,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           m = fmaxf(m, sj);
         }
         __syncwarp();
-        if (lane == 0) ATT_ARRIVE(&q_empty[qb]);
+        if (lane == 0) mbar_arrive(&q_empty[qb]);
       }
       tmem_ld_wait();
       TICK(6);
@@ -562,7 +550,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) ATT_ARRIVE(&p_full[u]);
+      if (lane == 0) mbar_arrive(&p_full[u]);
       TICK(3);
     }
     TICK(4);
@@ -576,7 +564,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int is = 0; is < my_items; ++is) {
       const int it = blockIdx.x + is * gridDim.x;
       const int b = it / H, h = it % H, kb = is & 1;
-      ATT_WAIT(&kv_full[kb], (is >> 1) & 1);
+      mbar_wait(&kv_full[kb], (is >> 1) & 1);
       const uint8_t* sK = smem + A::OFF_K + kb * A::KV_BYTES;
       const uint8_t* sV = smem + A::OFF_V + kb * A::KV_BYTES;
       for (int r = 0; r < side_rows; ++r) {
@@ -626,7 +614,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         __syncwarp();
       }
       __syncwarp();
-      if (lane == 0) ATT_ARRIVE(&kv_empty[kb]);
+      if (lane == 0) mbar_arrive(&kv_empty[kb]);
     }
   }
   tc_fence_before();

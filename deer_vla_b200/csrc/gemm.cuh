@@ -60,27 +60,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Relaxed arrive (CTA scope): the waiter only needs what the program already guarantees before the arrive (tcgen05 loads / stores
-// retired behind tcgen05.wait + fence::before_thread_sync, shared-memory reads consumed); the default .release would also hold the
-// arrive until this thread's earlier GLOBAL stores have drained.
-__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// try_wait without a suspend-time hint: returns after the (short) implementation-defined window; for waits that sit on a critical
-// path of a few hundred cycles, where the wake-up latency of a long suspend would show.
-__device__ __forceinline__ bool mbar_try_wait_nohint(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
 // non-blocking: has the phase with this parity completed?
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -94,12 +73,6 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait_nohint(bar, parity)) {
-    if (++spins > (1u << 28)) __trap();
-  }
 }
 // Bounded wait: a protocol bug must surface as a launch failure (trap), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -384,11 +357,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-#ifdef DEER_ATTN_RELAXED
-      if (lane == 0) mbar_arrive_relaxed(&tempty_bar[as]);
-#else
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
-#endif
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
   }
