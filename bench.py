@@ -71,38 +71,94 @@ def emit(line: dict):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md).
+    One streaming `nvidia-smi -lms 50` process started before the warm-up; every row carries nvidia-smi's own timestamp and only
+    rows inside [mark_begin, mark_end] are kept (a poll-per-query loop got 1-6 samples into a 0.8 s region).  Falls back to
+    polling if the stream yields nothing."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.stop_flag, self.t = index, [], False, None
+        self.index, self.rows, self.stop_flag, self.t, self.proc = index, [], False, None, None
+        self.t_begin, self.t_end = None, None
 
-    def _run(self):
+    def _cmd(self, loop_ms=None):
+        c = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)]
+        return c + ["-lms", str(loop_ms)] if loop_ms else c
+
+    @staticmethod
+    def _ts(field: str):
+        import datetime
+        try:
+            return datetime.datetime.strptime(field.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except Exception:
+            return None
+
+    def _add(self, line: str):
+        f = [x.strip() for x in line.strip().split(",")]
+        if len(f) >= 8:
+            self.rows.append((self._ts(f[0]), time.time(), f[1:]))
+
+    def _stream(self):
+        try:
+            self.proc = subprocess.Popen(self._cmd(50), stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
+            for line in self.proc.stdout:
+                self._add(line)
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def _poll(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                out = subprocess.run(self._cmd(), capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                    self._add(out.splitlines()[0])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def start(self):
-        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t = threading.Thread(target=self._stream, daemon=True)
         self.t.start()
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+        if not self.rows:                      # the stream produced nothing so far: poll as well
+            self.t2 = threading.Thread(target=self._poll, daemon=True)
+            self.t2.start()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         self.stop_flag = True
-        if self.t:
-            self.t.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        for th in (self.t, getattr(self, "t2", None)):
+            if th:
+                th.join(timeout=6)
+        b, e = self.t_begin, self.t_end
+        def inside(r):
+            ts = r[0] if r[0] is not None else r[1]
+            return b is None or e is None or (b - 0.05 <= ts <= e + 0.05)
+        rows = [r[2] for r in self.rows if inside(r)] or [r[2] for r in self.rows[-3:]]
+        def num(x):
+            try:
+                return float(x)
+            except Exception:
+                return None
+        sm = [v for v in (num(r[0]) for r in rows) if v is not None]
+        mx = [v for v in (num(r[1]) for r in rows) if v is not None]
+        pw = [v for v in (num(r[2]) for r in rows) if v is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "power_w": float(np.median(pw)) if pw else None, "reasons": reasons, "samples": len(rows)}
 
 
 def measured_peaks():
@@ -218,14 +274,16 @@ def engine_arm(a):
 
     # ---- device-timed region ------------------------------------------------------------------
     eng.reset()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for t in range(a.warmup):
         r, g = frames[t % NF]
         eng.step(r, g, ids, mask, slots, want_delta=False)
     barrier()
     launches0 = eng.stats().kernel_launches_total
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     exit_hist = np.zeros(cfg.n_layers, dtype=np.int64)
     outs = []
@@ -241,6 +299,8 @@ def engine_arm(a):
     if ncu_range:
         torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
+    if rank == 0:
+        sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.stats().kernel_launches_total - launches0
     for o in outs:
