@@ -168,3 +168,33 @@ def test_assemble_state_dict_from_published_pieces():
         assert torch.equal(merged[k], want), k
     _, missing = assemble_state_dict(cfg, hf_lm=hf, clip=clip)
     assert any(m.startswith("perceiver.") for m in missing) and any(m.startswith("extra_exit.") for m in missing)
+
+
+def test_gelu_epilogue_polynomial_constants():
+    """The constants of the one-MUFU exact GELU that ships in csrc/common.cuh (gelu_erf_fast), evaluated here in float32 with the
+    same Horner order, reproduce 0.5 x (1 + erf(x / sqrt 2)) -- nn.GELU() of the reference's FeedForward (helpers.py:15-22) and
+    MPT MLP -- to <= 1e-6 absolute on [-8, 8] and keep relative accuracy in the negative tail.  (The GPU test
+    test_gemm_epilogue_gelu_is_exact_erf_gelu checks the kernel itself.)"""
+    import math
+    import os
+    import re
+    import numpy as np
+    src = open(os.path.join(os.path.dirname(__file__), "..", "deer_vla_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("float gelu_erf_fast(float x)"):]
+    body = body[:body.index("return")]
+    first = float(re.search(r"float p = ([-+0-9.e]+)f;", body).group(1))
+    rest = [float(x) for x in re.findall(r"p = fmaf\(p, a, ([-+0-9.e]+)f\);", body)]
+    clamp = float(re.search(r"fminf\(fabsf\(x\), ([0-9.]+)f\)", body).group(1))
+    assert len(rest) == 7 and rest[-1] == -1.0 and clamp == 6.0
+    x = np.linspace(-8, 8, 200001).astype(np.float32)
+    a = np.minimum(np.abs(x), np.float32(clamp))
+    p = np.full_like(a, np.float32(first))
+    for c in rest:
+        p = (p * a + np.float32(c)).astype(np.float32)
+    xt = x * np.exp2(p).astype(np.float32)
+    got = np.where(x >= 0, x - xt, xt).astype(np.float64)
+    xd = x.astype(np.float64)
+    ref = np.array([0.5 * v * (1.0 + math.erf(v / math.sqrt(2.0))) for v in xd])
+    assert np.abs(got - ref).max() <= 1e-6
+    tail = (xd < -3) & (xd > -6)
+    assert (np.abs(got - ref)[tail] / np.abs(ref[tail])).max() <= 2e-4
