@@ -63,7 +63,7 @@ static bool make_tmap(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t 
 
 // Launch with (optionally) programmatic stream serialization: the kernel may begin while its predecessor drains; the kernels
 // launched this way all start with pdl_wait() (common.cuh).  DEER_PDL=0 turns it off (A/B), and it is never used during graph capture.
-static bool g_pdl_env = getenv("DEER_PDL") ? atoi(getenv("DEER_PDL")) != 0 : true;
+static bool g_launch_overlap = getenv("DEER_PDL") ? atoi(getenv("DEER_PDL")) != 0 : true;
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -71,7 +71,7 @@ static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = (pdl && g_pdl_env) ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = (pdl && g_launch_overlap) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
@@ -1384,8 +1384,8 @@ extern "C" int deer_get_tap(deer_ctx* c, const char* name, int layer, float* out
 }
 
 extern "C" int deer_set_launch_overlap(int enable) {
-  const int prev = g_pdl_env ? 1 : 0;
-  g_pdl_env = enable != 0;
+  const int prev = g_launch_overlap ? 1 : 0;
+  g_launch_overlap = enable != 0;
   return prev;
 }
 
