@@ -387,11 +387,12 @@ def golden_generate(bs=2, win=12, S=16):
                         episodes=np.array(eps), window=win, S=S)
 
 
-def golden_yardstick(S=32, T=2):
-    """Rounding yardstick at OpenFlamingo-3B size: the oracle in fp32 and with bf16-rounded
-    contraction operands on the same inputs, full depth (every exit probed), 2 episodes x T steps -> yardstick3b.npz."""
+def golden_yardstick(S=32, T=2, family="3b"):
+    """Rounding yardstick at OpenFlamingo-3B / -9B size: the oracle in fp32 and with bf16-rounded
+    contraction operands on the same inputs, full depth (every exit probed), 2 episodes x T steps -> yardstick3b.npz /
+    yardstick9b.npz (python -m oracle.make_golden --yardstick-only [--family 9b])."""
     torch.set_num_threads(os.cpu_count())
-    cfg = O.config_3b(12)
+    cfg = O.config_3b(12) if family == "3b" else O.config_9b(12)
     W = O.synth_weights(cfg, 0)
     thr = [1e8] * cfg.n_thresholds
     out = {"S": S, "T": T}
@@ -412,7 +413,7 @@ def golden_yardstick(S=32, T=2):
     for e in (0, 1):
         print(f"[yardstick] ep{e}: |bf16ops - fp32| pose {np.abs(out[f'bf16ops_ep{e}_pose'] - out[f'fp32_ep{e}_pose']).max():.3e} "
               f"deltas {np.abs(out[f'bf16ops_ep{e}_deltas'] - out[f'fp32_ep{e}_deltas']).max():.3e}")
-    np.savez_compressed(os.path.join(GOLD, "yardstick3b.npz"), **out)
+    np.savez_compressed(os.path.join(GOLD, f"yardstick{family}.npz"), **out)
 
 
 if __name__ == "__main__":
@@ -420,10 +421,11 @@ if __name__ == "__main__":
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--yardstick-only", action="store_true")
     ap.add_argument("--generate-only", action="store_true")
+    ap.add_argument("--family", default="3b", choices=["3b", "9b"], help="size of the --yardstick-only fixture")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     if a.yardstick_only:
-        golden_yardstick()
+        golden_yardstick(family=a.family)
         sys.exit(0)
     if a.generate_only:
         golden_generate()
@@ -435,3 +437,4 @@ if __name__ == "__main__":
     if a.full:
         golden_full()
         golden_yardstick()
+        golden_yardstick(family="9b")
