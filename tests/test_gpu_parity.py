@@ -316,6 +316,43 @@ def test_full3b_bf16_vs_reference_golden(full3b, gold_full):
     eng.close()
 
 
+def test_full3b_deer_s_bf16_vs_reference_golden(full3b, gold_full):
+    """BASELINE configs[1] -- DeeR-S (max_layer=4 => 5 layers built, exits [1, 3], forced exit at 3; thresholds for exit_ratio 0.8)
+    on the tcgen05 product path vs the golden outputs of the UNMODIFIED reference (S_ep* of tests/golden/full3b.npz; the DeeR-B
+    checkpoint's weights loaded into the truncated model, strict=False, like eval_calvin.py:576-577)."""
+    ocfgB, WB = full3b
+    ocfg = O.config_3b(4)
+    W = {k: v for k, v in WB.items() if k in {n for n, _, _ in O.weight_specs(ocfg)}}
+    g = gold_full
+    S = int(g["S"])
+    thr = g["thresholds_S"].tolist()
+    eng = _engine(ocfg, W, max_batch=2, max_seq=S, precision="bf16", gemm_impl="tcgen05")
+    eng.set_thresholds(thr)
+    eng.reset()
+    exits = [e for e in ocfg.exit_list if e <= ocfg.ctrl_max_layer]
+    assert exits == [1, 3] and len(thr) == 2
+    worst_pose, n_dec = 0.0, 0
+    diverged = [False, False]
+    for t in range(3):
+        rgb, grip, ids = _inputs(ocfg, [0, 1], t, S)
+        out = eng.step(rgb.cuda(), grip.cuda(), ids.cuda())
+        ex, pose = out["exit_layer"].cpu().numpy(), out["pose"].cpu().numpy()
+        for e in range(2):
+            if diverged[e]:
+                continue                      # after a rounding-level exit flip the carried LSTM state legitimately differs
+            gd, gex = g[f"S_ep{e}_deltas"][t], int(g[f"S_ep{e}_exit_layer"][t])
+            margin = min(abs(gd[k] - thr[k]) for k in range(len(exits)) if not np.isnan(gd[k]))
+            n_dec += 1
+            if int(ex[e]) == gex:
+                worst_pose = max(worst_pose, float(np.abs(pose[e] - g[f"S_ep{e}_pose"][t]).max()))
+            else:
+                assert margin <= 0.02, f"exit flip outside the rounding margin: ep{e} t{t} got {ex[e]} want {gex} margin {margin}"
+                diverged[e] = True
+    assert n_dec >= 2 and worst_pose <= 5e-2, (n_dec, worst_pose)
+    print(f"\n[full3b DeeR-S bf16] worst pose |err| {worst_pose:.3e} over {n_dec} decisions")
+    eng.close()
+
+
 def test_full3b_bf16_within_rounding_yardstick(full3b):
     """'bf16 tolerance' made concrete: the oracle with bf16-rounded contraction operands (fp32
     accumulate, everything else fp32) differs from the fp32 oracle by Y on these inputs; the engine's bf16 path must be
