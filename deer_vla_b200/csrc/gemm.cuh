@@ -437,7 +437,11 @@ __device__ __forceinline__ float4 epi_math4(float4 t, float4 b, float sc) {
   t.z = act_fast<ACT>(t.z + b.z) * sc; t.w = act_fast<ACT>(t.w + b.w) * sc;
   return t;
 }
-template <int ACT>
+// DEEP (instantiated for ACT_NONE only -- every residual GEMM of the model): all eight fp32 residual row segments of the chunk
+// are requested at once, as soon as the accumulator registers are free (4 KB per warp in flight).  The shallow form requests four
+// at a time and waits for each batch before its stores: two serialized HBM round trips per 32 x 32 chunk, which made the residual
+// GEMMs latency-bound at 4.4 TB/s.  (Deep loads in every activation variant spill at this kernel's register budget.)
+template <int ACT, bool DEEP>
 __device__ __forceinline__ void epi_store_coalesced_t(const GemmEpi& e, float sc, int row0, int col0, int M, int N, float (&v)[32],
                                                       float* stage, int lane) {
   const bool fullc = (col0 + 32 <= N);
@@ -448,6 +452,33 @@ __device__ __forceinline__ void epi_store_coalesced_t(const GemmEpi& e, float sc
   if (vec_ok && e.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + c4));
 #pragma unroll
   for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stage + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  if (DEEP && vec_ok) {
+    float4 rs[8];                             // v[] is dead from here on
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row0 + it * 4 + sub;
+      rs[it] = (has_res && row < M) ? *reinterpret_cast<const float4*>(e.resid + static_cast<size_t>(row) * e.ldr + col0 + c4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + sub;
+      const int row = row0 + rr;
+      float4 t = epi_math4<ACT>(*reinterpret_cast<const float4*>(stage + rr * 36 + c4), b4, sc);
+      if (row < M) {
+        t.x += rs[it].x; t.y += rs[it].y; t.z += rs[it].z; t.w += rs[it].w;
+        if (e.out_f32) {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.C) + static_cast<size_t>(row) * e.ldc + col0 + c4) = t;
+        } else {
+          uint2 o; o.x = pack_bf16x2(t.x, t.y); o.y = pack_bf16x2(t.z, t.w);
+          *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.C) + static_cast<size_t>(row) * e.ldc + col0 + c4) = o;
+        }
+      }
+    }
+    __syncwarp();
+    return;
+  }
   __syncwarp();
   if (vec_ok) {
     // v[] is dead from here on: the residual rows are fetched in two batches of four 128-byte row segments per 8 lanes
@@ -495,10 +526,12 @@ __device__ __forceinline__ void epi_store_coalesced_t(const GemmEpi& e, float sc
 }
 __device__ __forceinline__ void epi_store_coalesced(const GemmEpi& e, float sc, int row0, int col0, int M, int N, float (&v)[32],
                                                     float* stage, int lane) {
-  if (e.act == ACT_NONE) epi_store_coalesced_t<ACT_NONE>(e, sc, row0, col0, M, N, v, stage, lane);
-  else if (e.act == ACT_GELU) epi_store_coalesced_t<ACT_GELU>(e, sc, row0, col0, M, N, v, stage, lane);
-  else if (e.act == ACT_QUICKGELU) epi_store_coalesced_t<ACT_QUICKGELU>(e, sc, row0, col0, M, N, v, stage, lane);
-  else epi_store_coalesced_t<ACT_RELU>(e, sc, row0, col0, M, N, v, stage, lane);
+  if (e.act == ACT_NONE) {
+    if (e.resid != nullptr) epi_store_coalesced_t<ACT_NONE, true>(e, sc, row0, col0, M, N, v, stage, lane);
+    else epi_store_coalesced_t<ACT_NONE, false>(e, sc, row0, col0, M, N, v, stage, lane);
+  } else if (e.act == ACT_GELU) epi_store_coalesced_t<ACT_GELU, false>(e, sc, row0, col0, M, N, v, stage, lane);
+  else if (e.act == ACT_QUICKGELU) epi_store_coalesced_t<ACT_QUICKGELU, false>(e, sc, row0, col0, M, N, v, stage, lane);
+  else epi_store_coalesced_t<ACT_RELU, false>(e, sc, row0, col0, M, N, v, stage, lane);
 }
 
 struct GemmTc2 {
