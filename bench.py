@@ -206,7 +206,7 @@ def reference_arm(a):
         return
     fam, max_layer, exit_ratio, desc = workload(a)
     r = run_cpu_reference(workload(a), a.steps, a.warmup, a.seq)
-    line = {"impl": "reference", "metric": "action-steps/sec", "value": r["value"], "unit": "action-steps/s", "n_gpus": a.gpus,
+    line = {"impl": "reference", "metric": "action-steps/sec (device-timed)", "value": r["value"], "unit": "action-steps/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "batch_per_step": 1, "seq_len": a.seq, "max_layer": max_layer, "exit_ratio": exit_ratio,
@@ -417,7 +417,7 @@ def engine_arm(a):
         r = run_cpu_reference(workload(a), a.cpu_steps, 1, S)
         cpu_base = {"value": r["value"], "unit": "action-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     if rank == 0:
-        line = {"metric": "action-steps/sec", "value": value, "unit": "action-steps/s", "n_gpus": world, "steps": a.steps,
+        line = {"metric": "action-steps/sec (device-timed)", "value": value, "unit": "action-steps/s", "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": desc, "episodes_per_gpu": B, "seq_len": S, "max_layer": max_layer, "exit_ratio": exit_ratio,
