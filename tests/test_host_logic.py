@@ -198,3 +198,41 @@ def test_gelu_epilogue_polynomial_constants():
     assert np.abs(got - ref).max() <= 1e-6
     tail = (xd < -3) & (xd > -6)
     assert (np.abs(got - ref)[tail] / np.abs(ref[tail])).max() <= 2e-4
+
+
+def test_bench_clock_sampler_keeps_only_samples_inside_the_timed_region(tmp_path, monkeypatch):
+    """bench.py's ClockSampler streams `nvidia-smi -lms 50` and keeps the rows whose nvidia-smi timestamp falls inside
+    [mark_begin, mark_end] (the driver rejects a line without clocks sampled DURING the timed region).  Driven here with a fake
+    nvidia-smi: rows before the region carry a different clock and must not leak into the median."""
+    import importlib
+    import os
+    import stat
+    import sys
+    import time
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("""#!/usr/bin/env python3
+import sys, time, datetime
+loop = "-lms" in sys.argv
+t0 = time.time()
+while True:
+    ts = datetime.datetime.now().strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+    clk = 1965 if time.time() - t0 < 0.35 else 1400
+    print(f"{ts}, {clk}, 1965, 990.0, Not Active, Not Active, Not Active, {'Not Active' if clk == 1965 else 'Active'}", flush=True)
+    if not loop:
+        break
+    time.sleep(0.05)
+""")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.environ["PATH"])
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    bench = importlib.import_module("bench")
+    s = bench.ClockSampler(0)
+    s.start()
+    time.sleep(0.6)                      # "warm-up": the fake reports 1965 MHz for the first 0.35 s
+    s.mark_begin()
+    time.sleep(0.5)
+    s.mark_end()
+    out = s.stop()
+    assert out["samples"] >= 5 and out["sm_mhz"] == 1400.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"] and out["power_w"] == 990.0
