@@ -4,10 +4,12 @@
   python bench.py --gpus N --steps K --warmup W            # engine arm (hand-written sm_100a path)
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
 
-One "step" = one action-step for every one of the B concurrent episodes on a GPU (B = --batch, default 224:
-BASELINE.json "224-seq batch").  value = action-steps/s over all ranks, device-timed with CUDA events,
-inputs resident in HBM.  e2e = the same through DeerEngine.step with HOST (pinned) buffers: H2D of both
-frames + tokens and D2H of actions/exit ids inside the timed region.
+One "step" = one action-step for every one of the B concurrent episodes on a GPU.  BASELINE.json configs[2] is "224-seq batch
+episode-sharded on 8xB200": 224 episodes IN TOTAL, split evenly over the ranks like the reference does
+(eval_utils.py:523-527: eval_sequences[rank*k:(rank+1)*k], k = NUM_SEQUENCES / device_num) -- B = 224 // N per GPU,
+"scaling": "strong".  --weak keeps 224 episodes per GPU (the round-1 reading; extra, not the headline); --batch overrides B.
+value = action-steps/s over all ranks, device-timed with CUDA events, inputs resident in HBM.  e2e = the same through
+DeerEngine.step with HOST (pinned) buffers: H2D of both frames + tokens and D2H of actions/exit ids inside the timed region.
 """
 from __future__ import annotations
 
@@ -237,35 +239,49 @@ def engine_arm(a):
         dist.init_process_group("nccl", device_id=dev)
     fam, max_layer, exit_ratio, desc = workload(a)
     cfg = config_3b(max_layer) if fam == "3b" else config_9b(max_layer)
-    B, S = a.batch, a.seq
+    if a.batch is not None:
+        B, scaling = a.batch, "weak"
+    elif a.weak:
+        B, scaling = a.episodes, "weak"
+    else:
+        assert a.episodes % world == 0, "NUM_SEQUENCES % device_num == 0 (eval_utils.py:523)"
+        B, scaling = a.episodes // world, "strong"
+    S = a.seq
     eng = DeerEngine(cfg, max_batch=B, max_slots=B, max_seq=S, device=local, precision="bf16", gemm_impl="tcgen05", use_graph=a.graph)
     t0 = time.time()
     eng.load_state_dict(synth_state_items(cfg, 0))
     t_load = time.time() - t0
+    weight_gb = eng.stats().weight_bytes / 1e9
 
     # synthetic inputs: NF distinct frame sets per camera (each step's input set is 2*B*3*224*224*4 B = 270 MB at B=224,
     # larger than the 126 MB L2, and consecutive steps use different sets) ; episodes sharded by rank (eval_utils.py:523-527)
-    NF = 4
+    NF = 6
     frames = [(synth_frames(cfg, B, 1000 + 17 * (rank * NF + i), dev), synth_frames(cfg, B, 5000 + 17 * (rank * NF + i), dev)) for i in range(NF)]
     ids = synth_instruction_ids(cfg, B, S, seed=2000 + rank).to(dev)
     mask = torch.ones(B, S, dtype=torch.uint8, device=dev)
     slots = torch.arange(B, dtype=torch.int32, device=dev)
 
-    # thresholds: GPU calibration (full-depth delta table) + the reference's greedy solver (value_net.py:203-264)
+    # thresholds: the reference's calibration pass in its own (training-window) layout on the GPU -- generate mode, a random exit
+    # layer standing in for every past frame (value_net.py:300-399, flamingo_mpt.py:476-492) -- over windows built from the SAME
+    # frame sets the timed steps read, then the reference's greedy solver (value_net.py:203-264).  The deltas are taken at
+    # window positions 5..10 from a zero LSTM state, and the timed region below covers the same timestep range of an episode.
+    from deer_vla_b200.value_net import exit_probabilities, generate_action_values_window
     ctrl = ExitController(None, exit_id_list=eng.exit_list, steps_per_stage=1, exit_dist="exp", leq=True, max_layer=max_layer, engine=eng)
-    eng.reset()
+    WIN = 12
+    gen = torch.Generator().manual_seed(4242 + rank)
     cols = []
-    for t in range(a.calib_steps):
-        r, g = frames[t % NF]
-        out = eng.step(r, g, ids, mask, slots, full_depth=True)
-        cols.append(out["delta"].float().t().cpu())
-    table = torch.cat(cols, dim=1)
+    for w in range(a.calib_windows):
+        order = [(w * 5 + t) % NF for t in range(WIN)]
+        win = {"rgb": torch.stack([frames[i][0] for i in order], dim=1), "gripper": torch.stack([frames[i][1] for i in order], dim=1), "ids": ids}
+        cols.append(generate_action_values_window(eng, [win], window_size=WIN, generator=gen))
+        del win
+    table = torch.cat(cols, dim=1)                 # (len(exit_list), B * 6 * windows)
     if world > 1:                                  # the reference all_gathers the per-rank tables (value_net.py:195-201)
-        tl = [torch.zeros_like(table).to(dev) for _ in range(world)]
-        dist.all_gather(tl, table.to(dev))
-        table = torch.cat([x.cpu() for x in tl], dim=1)
+        from deer_vla_b200.sharding import all_gather_values
+        table = all_gather_values(table)
     ctrl.set_threshold(None, None, None, exit_ratio, cfg.llm_name, values=table)
     thresholds = [ctrl.thresholds[e] for e in ctrl._real_exits()]
+    target_probs = [float(x) for x in exit_probabilities(len(thresholds), exit_ratio, "exp", cfg.llm_name)]
 
     def barrier():
         if world > 1:
@@ -277,7 +293,8 @@ def engine_arm(a):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for t in range(a.warmup):
+    lead_in = max(0, 5 - a.warmup)                 # untimed: puts the timed steps at episode timesteps >= 5 (the calibrated range)
+    for t in range(lead_in + a.warmup):
         r, g = frames[t % NF]
         eng.step(r, g, ids, mask, slots, want_delta=False)
     barrier()
@@ -292,7 +309,7 @@ def engine_arm(a):
         torch.cuda.profiler.start()
     e0.record()
     for t in range(a.steps):
-        r, g = frames[(a.warmup + t) % NF]
+        r, g = frames[(lead_in + a.warmup + t) % NF]
         outs.append(eng.step(r, g, ids, mask, slots, want_delta=False))
     e1.record()
     barrier()
@@ -365,10 +382,12 @@ def engine_arm(a):
             continue                                   # first profiled step creates the events
         if prof_acc is None:
             prof_acc = {"gemm_ms": dict.fromkeys(p["gemm_ms"], 0.0), "gemm_flops": dict.fromkeys(p["gemm_ms"], 0.0),
+                        "gemm_bytes": dict.fromkeys(p["gemm_ms"], 0.0),
                         "gemm_launches": dict.fromkeys(p["gemm_ms"], 0), "step_ms": 0.0, "n": 0}
         for k in p["gemm_ms"]:
             prof_acc["gemm_ms"][k] += p["gemm_ms"][k]
             prof_acc["gemm_flops"][k] += p["gemm_flops"][k]
+            prof_acc["gemm_bytes"][k] += p["gemm_bytes"][k]
             prof_acc["gemm_launches"][k] += p["gemm_launches"][k]
         prof_acc["step_ms"] += p["step_ms"]
         prof_acc["n"] += 1
@@ -382,15 +401,21 @@ def engine_arm(a):
     stages = {k: {"ms_per_step": prof_acc["gemm_ms"][k] / prof_acc["n"],
                   "tflops": (prof_acc["gemm_flops"][k] / (prof_acc["gemm_ms"][k] * 1e-3) / 1e12) if prof_acc["gemm_ms"][k] > 0 else 0.0,
                   "launches_per_step": prof_acc["gemm_launches"][k] // prof_acc["n"]} for k in prof_acc["gemm_ms"]}
-    traffic, tensor_pct = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if os.path.exists(tp) and a.workload == "deer_b" and B == 224:      # ncu capture of exactly this workload (committed summary)
+    g_by = sum(prof_acc["gemm_bytes"].values())
+    # `traffic` is an ncu figure (dram__bytes_read.sum + dram__bytes_write.sum per launch); it cannot be measured inside this run, so
+    # it is reported ONLY when a committed capture of exactly this command exists, and labelled static; the live number beside it
+    # is the algorithmic bytes per launch computed from the GEMM shapes this run launched.
+    traffic, traffic_src, tensor_pct = None, None, None
+    tp = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
+    if os.path.exists(tp):
         tj = json.load(open(tp))
-        traffic, tensor_pct = tj["traffic_bytes_per_launch"], tj["tensor_pipe_active_pct_time_weighted"]
+        if tj.get("workload") == a.workload and tj.get("episodes_per_gpu") == B:
+            traffic, tensor_pct = tj["traffic_bytes_per_launch"], tj.get("tensor_pipe_active_pct_time_weighted")
+            traffic_src = f"static_from: profiles/r02_gemm_traffic.json ({tj.get('captured_at', 'ncu --set full capture of this command')})"
     roofline = {"bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel<BN> (tcgen05.mma + TMA; every GEMM launch of a step)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
-                "traffic_source": "profiles/r01_gemm_traffic.json (ncu dram__bytes_read+write per launch)" if traffic else None,
-                "tensor_pipe_active_pct_ncu": tensor_pct,
+                "traffic_source": traffic_src, "tensor_pipe_active_pct_ncu_static": tensor_pct,
+                "algorithmic_bytes_per_launch": g_by / max(1, g_n),
                 "peak_source": peak_src, "algorithmic_flops_per_launch": g_fl / max(1, g_n),
                 "avg_launch_ms": g_ms / max(1, g_n), "gemm_share_of_step": g_ms / prof_acc["step_ms"] if prof_acc["step_ms"] else None,
                 "stages": stages, "active_after_each_exit": prof_acc.get("active_after")}
@@ -418,16 +443,23 @@ def engine_arm(a):
         cpu_base = {"value": r["value"], "unit": "action-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     if rank == 0:
         line = {"metric": "action-steps/sec (device-timed)", "value": value, "unit": "action-steps/s", "n_gpus": world, "steps": a.steps,
-                "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": desc, "episodes_per_gpu": B, "seq_len": S, "max_layer": max_layer, "exit_ratio": exit_ratio,
-                           "parallelism": f"episode-sharded replicas x{world}", "thresholds": thresholds,
-                           "l2": "each step reads a different 270 MB frame set (> 126 MB L2); weights 3.1 GB",
+                "config": {"workload": desc, "episodes_total": B * world, "episodes_per_gpu": B, "seq_len": S, "max_layer": max_layer,
+                           "exit_ratio": exit_ratio, "parallelism": f"episode-sharded replicas x{world} (eval_utils.py:523-527)",
+                           "thresholds": thresholds,
+                           "l2": f"each step reads a different {2 * B * 3 * cfg.image_size ** 2 * 4 / 1e6:.0f} MB frame set; every step streams "
+                                 f"the {weight_gb:.1f} GB of weights (> 126 MB L2)",
                            "weights": "seeded synthetic (no checkpoints offline)", "calibration_samples": int(table.shape[1]),
-                           "cuda_graph": bool(a.graph)},
+                           "calibration": "generate-mode windows of 12 frames over the timed frame sets (value_net.py:300-399), deltas at window "
+                                          "positions 5..10; timed steps are episode timesteps >= 5 with carried LSTM state",
+                           "lead_in_steps": lead_in, "cuda_graph": bool(a.graph)},
                 "e2e": {"value": e2e_value, "unit": "action-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "e2e_raw_frames": e2e_u8, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
                 "exit_histogram": {str(e): int(exit_hist[e]) for e in exits_sorted},
+                "exit_fraction_target_vs_achieved": {str(e): [round(target_probs[i], 4), round(float(exit_hist[e]) / max(1, total_steps), 4)]
+                                                     for i, e in enumerate(exits_sorted)},
+                "step_algorithmic_frac_of_peak": step_tflops / peak_tf,
                 "mean_exit_depth_layers": float(sum((e + 1) * exit_hist[e] for e in exits_sorted) / max(1, total_steps)),
                 "step_algorithmic_tflops": step_tflops, "weights_load_s": t_load,
                 "gathered_rows": int(gathered.shape[0])}
@@ -446,9 +478,11 @@ def main():
     ap.add_argument("--workload", default="deer_b", choices=list(WORKLOADS))
     ap.add_argument("--max-layer", type=int, default=None, help="override the workload's max_layer (C5 sweep)")
     ap.add_argument("--exit-ratio", type=float, default=None, help="override the workload's exit_ratio (C5 sweep)")
-    ap.add_argument("--batch", type=int, default=224, help="concurrent episodes per GPU")
+    ap.add_argument("--episodes", type=int, default=224, help="episodes of the whole job (BASELINE configs: 224-seq batch), sharded over the ranks")
+    ap.add_argument("--weak", action="store_true", help="--episodes PER GPU instead of in total (weak scaling; not the BASELINE configs[2] reading)")
+    ap.add_argument("--batch", type=int, default=None, help="override: concurrent episodes per GPU")
     ap.add_argument("--seq", type=int, default=32)
-    ap.add_argument("--calib-steps", type=int, default=8)
+    ap.add_argument("--calib-windows", type=int, default=2, help="12-frame calibration windows per episode (6 delta samples each)")
     ap.add_argument("--cpu-steps", type=int, default=24, help="batch-1 oracle steps timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true", help="replay each step as one CUDA graph with conditional exit nodes (latency mode)")

@@ -77,9 +77,11 @@ def config_from_checkpoint(ckpt: Mapping[str, Any], path: str = "", max_layer: O
     unsupported = []
     if a["head_type"] != "deterministic":
         unsupported.append(f"head_type={a['head_type']}")
-    if not (a["mlp_layernorm"] and a["lstm_layernorm"] and a["mlp_num_hidden_layers"] == 2 and a["dropout_mode"] == "layerwise"):
-        unsupported.append("head variant other than the trained DeeR config (layerwise dropout, LayerNorm MLP/LSTM, 2 hidden layers; "
-                           "train_calvin_post_strategy.py:336-344)")
+    n_hidden = head_num_hidden_layers(a)
+    if n_hidden not in (2, 3):
+        unsupported.append(f"mlp_num_hidden_layers={n_hidden} (the engine builds 2 or 3 hidden layers)")
+    if a["dropout_mode"] not in ("layerwise", "last", "wo_last"):
+        unsupported.append(f"dropout_mode={a['dropout_mode']}")
     if a["pooling"] != "max":
         unsupported.append(f"pooling={a['pooling']}")
     for k in ("use_state", "sep_resampler", "residual", "tcp_rel", "no_image_patch"):
@@ -92,7 +94,57 @@ def config_from_checkpoint(ckpt: Mapping[str, Any], path: str = "", max_layer: O
     build = config_9b if "mpt_9b" in flags["llm_name"] else config_3b
     return build(a["max_layer"], ckpt_early_exit_layer=a["early_exit_layer"], exit_interval=a["exit_interval"],
                  lstm_layers=a["lstm_num_layers"], steps_per_stage=steps_per_stage, threshold_type=threshold_type,
-                 llm_name=flags["llm_name"])
+                 llm_name=flags["llm_name"], mlp_dims=tuple(MLP_HIDDEN_DIMS[:n_hidden]),
+                 mlp_layernorm=bool(a["mlp_layernorm"]), lstm_layernorm=bool(a["lstm_layernorm"]))
+
+
+MLP_HIDDEN_DIMS = (1024, 512, 256)                 # action_head.py:87,188
+
+
+def head_num_hidden_layers(a: Mapping[str, Any]) -> int:
+    """Hidden layers MLPTanhHead / MLPSigmoidHead actually build: ``mlp_num_hidden_layers`` for dropout_mode 'last' /
+    'layerwise', always 3 for the older hard-coded Sequentials ('wo_last'; action_head.py:116-158)."""
+    return int(a["mlp_num_hidden_layers"]) if a["dropout_mode"] in ("last", "layerwise") else 3
+
+
+def head_key_map(a: Mapping[str, Any]) -> Dict[str, str]:
+    """``nn.Sequential`` index of every parametrised module of the MLP heads for this checkpoint's head variant -> the
+    index the engine uses (the 'layerwise' layout: Linear 4j+1, LayerNorm 4j+2, output Linear 4n+1).  The reference builds a
+    different Sequential per (dropout_mode, layernorm, dropout > 0) (action_head.py:82-161, 183-269), so the same tensors
+    sit under different keys in checkpoints of different vintages."""
+    n, ln = head_num_hidden_layers(a), bool(a["mlp_layernorm"])
+    mode = a["dropout_mode"]
+    if mode == "layerwise":
+        lin = [4 * j + 1 for j in range(n)]; norm = [4 * j + 2 for j in range(n)]; out = 4 * n + 1
+    elif mode == "last":                          # [Linear, LN|Identity, ReLU] * n, Dropout after the last hidden layer
+        lin = [3 * j for j in range(n)]; norm = [3 * j + 1 for j in range(n)]; out = 3 * n + 1
+    elif ln:                                      # 'wo_last' with LayerNorm: Dropout, Linear, LN, ReLU, ... (3 hidden), Linear
+        lin = [1, 5, 9]; norm = [2, 6, 10]; out = 12
+    elif float(a.get("exit_dropout", 0.0)) > 0:   # Dropout, Linear, ReLU, ... : Linear at 1, 4, 7; output at 9
+        lin = [1, 4, 7]; norm = []; out = 9
+    else:                                         # the oldest layout: Linear, ReLU, ... : 0, 2, 4; output at 6
+        lin = [0, 2, 4]; norm = []; out = 6
+    m = {str(lin[j]): str(4 * j + 1) for j in range(n)}
+    if ln:
+        m.update({str(norm[j]): str(4 * j + 2) for j in range(n)})
+    m[str(out)] = str(4 * n + 1)
+    return m
+
+
+_HEAD_KEY = re.compile(r"^(module\.)?((?:extra_exit|lm_head)\.(?:actions|gripper)\.mlp\.)(\d+)(\.(?:weight|bias))$")
+
+
+def canonical_head_keys(sd: Mapping[str, Any], a: Mapping[str, Any]) -> Dict[str, Any]:
+    """Rename the MLP-head tensors of a checkpoint to the engine's canonical 'layerwise' indices (``head_key_map``);
+    everything else passes through."""
+    km = head_key_map(a)
+    out: Dict[str, Any] = {}
+    for k, v in sd.items():
+        m = _HEAD_KEY.match(k)
+        if m and m.group(3) in km:
+            k = f"{m.group(1) or ''}{m.group(2)}{km[m.group(3)]}{m.group(4)}"
+        out[k] = v
+    return out
 
 
 def state_dict_of(ckpt: Mapping[str, Any]) -> Mapping[str, Any]:

@@ -50,6 +50,9 @@ class DeerConfig:
     mlp_dims: Tuple[int, ...] = (1024, 512)
     threshold_type: str = "L2"
     steps_per_stage: int = 1
+    # head variants of older checkpoints (eval_calvin.py:464-476): mlp_dims (1024, 512, 256), no LayerNorms
+    mlp_layernorm: bool = True
+    lstm_layernorm: bool = True
 
     @property
     def early_exit_layer(self) -> int:          # eval_calvin.py:529

@@ -88,7 +88,7 @@ struct LaunchStats {
 // ---------------------------------------------------------------------------------------------
 // GEMM dispatch (shared by the engine and deer_op_gemm)
 // ---------------------------------------------------------------------------------------------
-struct GemmRec { cudaEvent_t e0, e1; int tag, epoch, m_host, m_mul, n, k; bool dyn; };
+struct GemmRec { cudaEvent_t e0, e1; int tag, epoch, m_host, m_mul, n, k; bool dyn; int in_es, out_es; bool has_res; };
 struct GemmCtx {
   std::map<TmapKey, CUtensorMap> tmaps;
   bool attr_set[4] = {false, false, false, false};
@@ -140,7 +140,8 @@ static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int
   cudaError_t e;
   GemmRec rec{};
   if (g.profile) {
-    rec = GemmRec{g.get_event(), g.get_event(), g.tag, g.epoch, M, m_mul, N, K, m_dev != nullptr};
+    rec = GemmRec{g.get_event(), g.get_event(), g.tag, g.epoch, M, m_mul, N, K, m_dev != nullptr, dtype == 1 ? 4 : 2,
+                  (dtype == 1 || epi.out_f32) ? 4 : 2, epi.resid != nullptr};
     cudaEventRecord(rec.e0, st);
   }
   if (dtype == 1 || impl == DEER_GEMM_SIMT) {
@@ -311,8 +312,9 @@ struct deer_ctx {
   void* wte = nullptr;
   std::vector<LlmLayerW> llm;
   std::vector<LstmLayerW> lstm;
-  void *w_mlp1 = nullptr, *w_mlp2_pose = nullptr, *w_mlp2_grip = nullptr;
+  void *w_mlp1 = nullptr, *w_mlp2_pose = nullptr, *w_mlp2_grip = nullptr, *w_mlp3_pose = nullptr, *w_mlp3_grip = nullptr;
   float *b_mlp1 = nullptr, *g_mlp1 = nullptr, *be_mlp1 = nullptr, *b_mlp2 = nullptr, *g_mlp2 = nullptr, *be_mlp2 = nullptr;
+  float *b_mlp3 = nullptr, *g_mlp3 = nullptr, *be_mlp3 = nullptr;
   float *w3_pose = nullptr, *b3_pose = nullptr, *w3_grip = nullptr, *b3_grip = nullptr;
   float* alibi = nullptr; float* thr_dev = nullptr;
   // workspace
@@ -323,6 +325,8 @@ struct deer_ctx {
   void *l_ln = nullptr, *l_q = nullptr, *l_kv = nullptr, *l_att = nullptr, *l_h = nullptr, *l_qkv = nullptr;
   void *a0 = nullptr, *a_rest = nullptr, *head_in = nullptr, *y1 = nullptr;
   float *gates = nullptr, *cand_h = nullptr, *cand_c = nullptr, *mlp1 = nullptr, *mlp2 = nullptr, *y2 = nullptr, *cur_pose = nullptr, *cur_grip = nullptr;
+  void* y2t = nullptr; float *mlp3 = nullptr, *y3 = nullptr;      // third hidden layer (old checkpoints)
+  float *pooled = nullptr, *o_feat = nullptr;                    // max-pooled exit feature: per active row / per episode at its exit
   float *h_state = nullptr, *c_state = nullptr; int* cur_exit_id = nullptr;
   EpisodeMeta meta[2];
   uint8_t* exit_flag = nullptr; int* src_of_new = nullptr; int* n_active = nullptr;   // n_active[2]
@@ -398,6 +402,7 @@ static int derive(deer_ctx* c) {
   if (f.d_model / f.n_heads > 128) return set_err(&c->err, DEER_E_INVALID, "LLM head_dim must be <= 128");
   if (f.lstm_hidden > 2048 || f.lstm_hidden % 8 || f.lstm_layers < 1) return set_err(&c->err, DEER_E_INVALID, "bad lstm config");
   if (f.mlp_dim0 % 8 || f.mlp_dim1 % 8 || f.mlp_dim0 > 4096 || f.mlp_dim1 > 4096) return set_err(&c->err, DEER_E_INVALID, "bad mlp dims");
+  if (f.mlp_dim2 < 0 || f.mlp_dim2 % 8 || f.mlp_dim2 > 4096) return set_err(&c->err, DEER_E_INVALID, "bad mlp_dim2");
   if (f.max_batch < 1 || f.max_batch > 1024) return set_err(&c->err, DEER_E_INVALID, "max_batch must be in [1,1024]");
   if (f.max_slots < 1 || f.max_seq < 1 || f.max_seq > 256) return set_err(&c->err, DEER_E_INVALID, "bad max_slots / max_seq");
   if (f.n_layers < 1 || f.exit_interval < 1 || f.max_layer < 1) return set_err(&c->err, DEER_E_INVALID, "bad exit config");
@@ -448,7 +453,8 @@ static void build_required(deer_ctx* c) {
   r.push_back("perceiver.norm.weight");
   r.push_back("perceiver.norm.bias");
   r.push_back("lang_encoder.transformer.wte.weight");
-  for (int i = 0; i <= c->ctrl_max_layer; ++i) {
+  // every block the reference builds (flamingo_mpt.py:198): calibration runs to n_layers-1 and exit_id may name any of them
+  for (int i = 0; i < f.n_layers; ++i) {
     if ((i + 1) % f.cross_attn_every == 0)
       for (const char* s : {"attn.norm.weight", "attn.norm.bias", "attn.to_q.weight", "attn.to_kv.weight", "attn.to_out.weight", "attn_gate",
                             "ff.0.weight", "ff.0.bias", "ff.1.weight", "ff.3.weight", "ff_gate"}) {
@@ -469,30 +475,51 @@ static void build_required(deer_ctx* c) {
     }
   }
   for (int l = 0; l < f.lstm_layers; ++l) {
-    for (const char* s : {"weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"}) {
-      snprintf(b, sizeof(b), "extra_exit.rnn.layers.%d.%s", 3 * l, s);
-      r.push_back(b);
-    }
-    for (const char* s : {"weight", "bias"}) {
-      snprintf(b, sizeof(b), "extra_exit.rnn.layers.%d.%s", 3 * l + 1, s);
-      r.push_back(b);
-    }
-  }
-  for (const char* head : {"actions", "gripper"})
-    for (int idx : {1, 2, 5, 6, 9})
-      for (const char* s : {"weight", "bias"}) {
-        if (idx == 9 && false) continue;
-        snprintf(b, sizeof(b), "extra_exit.%s.mlp.%d.%s", head, idx, s);
+    if (f.lstm_layernorm) {                     // LayerNormLSTM: ModuleList [LSTM, LayerNorm, Dropout] per layer (action_head.py:15-40)
+      for (const char* s : {"weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"}) {
+        snprintf(b, sizeof(b), "extra_exit.rnn.layers.%d.%s", 3 * l, s);
         r.push_back(b);
       }
+      for (const char* s : {"weight", "bias"}) {
+        snprintf(b, sizeof(b), "extra_exit.rnn.layers.%d.%s", 3 * l + 1, s);
+        r.push_back(b);
+      }
+    } else {                                    // plain stacked nn.LSTM (action_head.py:71-79)
+      for (const char* s : {"weight_ih", "weight_hh", "bias_ih", "bias_hh"}) {
+        snprintf(b, sizeof(b), "extra_exit.rnn.%s_l%d", s, l);
+        r.push_back(b);
+      }
+    }
+  }
+  // MLP heads in the 'layerwise' Sequential layout (Linear at 4j+1, LayerNorm at 4j+2, output Linear at 4n+1); the host
+  // side renames the other dropout_mode layouts to this one (checkpoint.py)
+  const int nh = f.mlp_dim2 > 0 ? 3 : 2;
+  for (const char* head : {"actions", "gripper"}) {
+    for (int j = 0; j <= nh; ++j)
+      for (int part = 0; part < 2; ++part) {
+        if (part == 1 && (j == nh || !f.mlp_layernorm)) continue;
+        for (const char* s : {"weight", "bias"}) {
+          snprintf(b, sizeof(b), "extra_exit.%s.mlp.%d.%s", head, 4 * j + 1 + part, s);
+          r.push_back(b);
+        }
+      }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // C ABI: library level
 // ---------------------------------------------------------------------------------------------
 extern "C" int deer_abi_version(void) { return DEER_ABI_VERSION; }
+#ifndef DEER_SRC_HASH
+#define DEER_SRC_HASH "unhashed"
+#endif
+// The marker string lets build() read the hash out of the file without loading it.
+extern "C" const char* deer_source_hash(void) {
+  static const char marker[] = "DEER_SRC_HASH=" DEER_SRC_HASH;
+  return marker + 14;
+}
 extern "C" const char* deer_build_info(void) {
-  return "deer_engine sm_100a (tcgen05/TMEM/TMA GEMM, mma.sync flash attention), built " __DATE__ " " __TIME__;
+  return "deer_engine sm_100a (tcgen05/TMEM/TMA GEMM + attention), built " __DATE__ " " __TIME__ " src=" DEER_SRC_HASH;
 }
 extern "C" const char* deer_last_error(deer_ctx* c) { return c ? c->err.c_str() : g_last_error.c_str(); }
 
@@ -538,7 +565,7 @@ extern "C" int deer_create(const deer_config* cfg, int device, deer_ctx** out) {
     WS(c->x[i], B * S * D * 4);
     WS(c->media[i], B * 2 * nl * Wd * es);
     WS(c->meta[i].orig, B * 4); WS(c->meta[i].slot, B * 4); WS(c->meta[i].valid_len, B * 4);
-    WS(c->meta[i].xmode, B * S); WS(c->meta[i].prev_pose, B * 6 * 4); WS(c->meta[i].use_prev, B);
+    WS(c->meta[i].xmode, B * S); WS(c->meta[i].prev_pose, B * 6 * 4); WS(c->meta[i].prev_grip, B * 4); WS(c->meta[i].use_prev, B);
   }
   WS(c->l_ln, B * S * D * es);
   WS(c->l_q, B * S * c->xin * es);
@@ -556,6 +583,9 @@ extern "C" int deer_create(const deer_config* cfg, int device, deer_ctx** out) {
   WS(c->mlp1, B * 2 * f.mlp_dim0 * 4);
   WS(c->mlp2, B * 2 * f.mlp_dim1 * 4);
   WS(c->y2, B * 2 * f.mlp_dim1 * 4);
+  if (f.mlp_dim2 > 0) { WS(c->y2t, B * 2 * f.mlp_dim1 * es); WS(c->mlp3, B * 2 * f.mlp_dim2 * 4); WS(c->y3, B * 2 * f.mlp_dim2 * 4); }
+  WS(c->pooled, B * D * 4);
+  WS(c->o_feat, B * D * 4);
   WS(c->cur_pose, B * 6 * 4);
   WS(c->cur_grip, B * 4);
   WS(c->h_state, (size_t)f.max_slots * LL * H * 4);
@@ -750,8 +780,8 @@ extern "C" int deer_finalize_weights(deer_ctx* c) {
   RET(pack_f32(c, "perceiver.norm.bias", {Wd}, &c->p_norm_b));
   // ---- LLM
   RET(pack_mat(c, "lang_encoder.transformer.wte.weight", f.vocab, D, &c->wte));
-  c->llm.resize(c->ctrl_max_layer + 1);
-  for (int i = 0; i <= c->ctrl_max_layer; ++i) {
+  c->llm.resize(f.n_layers);
+  for (int i = 0; i < f.n_layers; ++i) {
     LlmLayerW& w = c->llm[i];
     w.has_x = ((i + 1) % f.cross_attn_every == 0);
     if (w.has_x) {
@@ -790,19 +820,28 @@ extern "C" int deer_finalize_weights(deer_ctx* c) {
     LstmLayerW& w = c->lstm[l];
     memset(&w, 0, sizeof(w));
     w.in = (l == 0) ? (int)D : (int)H;
-    snprintf(b, sizeof(b), "extra_exit.rnn.layers.%d.", 3 * l);
-    const std::string p(b);
-    RET(pack_mat(c, p + "weight_ih_l0", 4 * H, w.in, &w.w_cat, w.in + H, 0));
-    RET(pack_mat(c, p + "weight_hh_l0", 4 * H, H, &w.w_cat, w.in + H, w.in));
+    std::string n_ih, n_hh, n_bi, n_bh;
+    if (f.lstm_layernorm) {
+      snprintf(b, sizeof(b), "extra_exit.rnn.layers.%d.", 3 * l);
+      const std::string p(b);
+      n_ih = p + "weight_ih_l0"; n_hh = p + "weight_hh_l0"; n_bi = p + "bias_ih_l0"; n_bh = p + "bias_hh_l0";
+    } else {
+      const std::string p = "extra_exit.rnn.", sfx = "_l" + std::to_string(l);
+      n_ih = p + "weight_ih" + sfx; n_hh = p + "weight_hh" + sfx; n_bi = p + "bias_ih" + sfx; n_bh = p + "bias_hh" + sfx;
+    }
+    RET(pack_mat(c, n_ih, 4 * H, w.in, &w.w_cat, w.in + H, 0));
+    RET(pack_mat(c, n_hh, 4 * H, H, &w.w_cat, w.in + H, w.in));
     std::vector<float> bi, bh;
-    RET(host_vec(c, p + "bias_ih_l0", {4 * H}, &bi)); RET(host_vec(c, p + "bias_hh_l0", {4 * H}, &bh));
+    RET(host_vec(c, n_bi, {4 * H}, &bi)); RET(host_vec(c, n_bh, {4 * H}, &bh));
     for (size_t k = 0; k < bi.size(); ++k) bi[k] += bh[k];
     RET(upload_f32(c, bi, &w.b_sum));
-    snprintf(b, sizeof(b), "extra_exit.rnn.layers.%d.", 3 * l + 1);
-    RET(pack_f32(c, std::string(b) + "weight", {H}, &w.ln_g)); RET(pack_f32(c, std::string(b) + "bias", {H}, &w.ln_b));
+    if (f.lstm_layernorm) {
+      snprintf(b, sizeof(b), "extra_exit.rnn.layers.%d.", 3 * l + 1);
+      RET(pack_f32(c, std::string(b) + "weight", {H}, &w.ln_g)); RET(pack_f32(c, std::string(b) + "bias", {H}, &w.ln_b));
+    }
   }
   {
-    const int64_t d0 = f.mlp_dim0, d1 = f.mlp_dim1;
+    const int64_t d0 = f.mlp_dim0, d1 = f.mlp_dim1, d2 = f.mlp_dim2, dl = d2 > 0 ? d2 : d1;
     const std::string pa = "extra_exit.actions.mlp.", pg = "extra_exit.gripper.mlp.";
     RET(pack_mat(c, pa + "1.weight", d0, H, &c->w_mlp1, H, 0, 0, 2 * d0));
     RET(pack_mat(c, pg + "1.weight", d0, H, &c->w_mlp1, H, 0, d0, 2 * d0));
@@ -815,11 +854,20 @@ extern "C" int deer_finalize_weights(deer_ctx* c) {
       return upload_f32(c, va, dst);
     };
     RET(cat2(pa + "1.bias", pg + "1.bias", d0, &c->b_mlp1));
-    RET(cat2(pa + "2.weight", pg + "2.weight", d0, &c->g_mlp1)); RET(cat2(pa + "2.bias", pg + "2.bias", d0, &c->be_mlp1));
     RET(cat2(pa + "5.bias", pg + "5.bias", d1, &c->b_mlp2));
-    RET(cat2(pa + "6.weight", pg + "6.weight", d1, &c->g_mlp2)); RET(cat2(pa + "6.bias", pg + "6.bias", d1, &c->be_mlp2));
-    RET(pack_f32(c, pa + "9.weight", {6, d1}, &c->w3_pose)); RET(pack_f32(c, pa + "9.bias", {6}, &c->b3_pose));
-    RET(pack_f32(c, pg + "9.weight", {1, d1}, &c->w3_grip)); RET(pack_f32(c, pg + "9.bias", {1}, &c->b3_grip));
+    if (f.mlp_layernorm) {
+      RET(cat2(pa + "2.weight", pg + "2.weight", d0, &c->g_mlp1)); RET(cat2(pa + "2.bias", pg + "2.bias", d0, &c->be_mlp1));
+      RET(cat2(pa + "6.weight", pg + "6.weight", d1, &c->g_mlp2)); RET(cat2(pa + "6.bias", pg + "6.bias", d1, &c->be_mlp2));
+    }
+    if (d2 > 0) {
+      RET(pack_mat(c, pa + "9.weight", d2, d1, &c->w_mlp3_pose));
+      RET(pack_mat(c, pg + "9.weight", d2, d1, &c->w_mlp3_grip));
+      RET(cat2(pa + "9.bias", pg + "9.bias", d2, &c->b_mlp3));
+      if (f.mlp_layernorm) { RET(cat2(pa + "10.weight", pg + "10.weight", d2, &c->g_mlp3)); RET(cat2(pa + "10.bias", pg + "10.bias", d2, &c->be_mlp3)); }
+    }
+    const std::string io = std::to_string(d2 > 0 ? 13 : 9);
+    RET(pack_f32(c, pa + io + ".weight", {6, dl}, &c->w3_pose)); RET(pack_f32(c, pa + io + ".bias", {6}, &c->b3_pose));
+    RET(pack_f32(c, pg + io + ".weight", {1, dl}, &c->w3_grip)); RET(pack_f32(c, pg + io + ".bias", {1}, &c->b3_grip));
   }
   CK(cudaDeviceSynchronize());
   for (auto& kv : c->staged) if (kv.second.dev) cudaFree(kv.second.dev);
@@ -1038,8 +1086,12 @@ template <typename T> struct StepImpl {
     const int D = f.d_model, H = f.lstm_hidden, LL = f.lstm_layers, Bm = f.max_batch, d0 = f.mlp_dim0, d1 = f.mlp_dim1;
     const int* nd = nact();
     const EpisodeMeta& m = c->meta[cur];
-    launch_k(maxpool_kernel<T>, dim3((D + 255) / 256, n), dim3(256), 0, st, c->gemm.pdl, c->x[cur], m.valid_len, tp(c->a0), D + H, f.debug_taps ? c->tap_pooled : nullptr, S, D, n, nd);
+    launch_k(maxpool_kernel<T>, dim3((D + 255) / 256, n), dim3(256), 0, st, c->gemm.pdl, c->x[cur], m.valid_len, tp(c->a0), D + H, c->pooled, S, D, n, nd);
     KLAUNCH_CHECK("maxpool");
+    if (f.debug_taps) {
+      tap_scatter_kernel<float><<<dim3(n, 1), 256, 0, st>>>(c->pooled, c->tap_pooled, nullptr, (size_t)D, n, nd);
+      KLAUNCH_CHECK("tap_pooled");
+    }
     launch_k(lstm_gather_h_kernel<T>, dim3(n, LL), dim3(256), 0, st, c->gemm.pdl, c->h_state, m.slot, tp(c->a0), D + H, D, tp(c->a_rest), 2 * H, LL, H, Bm, n, nd);
     KLAUNCH_CHECK("lstm_gather_h");
     for (int l = 0; l < LL; ++l) {
@@ -1052,13 +1104,41 @@ template <typename T> struct StepImpl {
       launch_k(lstm_cell_kernel<T>, dim3(n), dim3(256), 0, st, c->gemm.pdl, c->gates, c->c_state, m.slot, l, LL, c->cand_h, c->cand_c, w.ln_g, w.ln_b, y, y_ld, H, Bm, n, nd);
       KLAUNCH_CHECK("lstm_cell");
     }
-    // both MLP heads: [Linear, LN, ReLU] x2 fused across heads, then the tiny output layers
-    RET(gemm(c->head_in, H, Bm, c->w_mlp1, H, n, 2 * d0, H, c->mlp1, 2 * d0, 1, c->b_mlp1, ACT_NONE, nullptr, nullptr, 0, nd, 1));
-    RET(ln<float, T>(c->mlp1, d0, c->g_mlp1, c->be_mlp1, 2, d0, tp(c->y1), d0, LnMap{0, 0, 0}, nullptr, 0, 1, 2 * n, nd, 2));
-    RET(gemm(c->y1, 2 * d0, Bm, c->w_mlp2_pose, d0, n, d1, d0, c->mlp2, 2 * d1, 1, c->b_mlp2, ACT_NONE, nullptr, nullptr, 0, nd, 1));
-    RET(gemm(tp(c->y1) + d0, 2 * d0, Bm, c->w_mlp2_grip, d0, n, d1, d0, c->mlp2 + d1, 2 * d1, 1, c->b_mlp2 + d1, ACT_NONE, nullptr, nullptr, 0, nd, 1));
-    RET(ln<float, float>(c->mlp2, d1, c->g_mlp2, c->be_mlp2, 2, d1, c->y2, d1, LnMap{0, 0, 0}, nullptr, 0, 1, 2 * n, nd, 2));
-    launch_k(head_out_kernel, dim3(n), dim3(256), 0, st, c->gemm.pdl, c->y2, d1, c->w3_pose, c->b3_pose, c->w3_grip, c->b3_grip, c->cur_pose, c->cur_grip, n, nd);
+    // both MLP heads: [Linear, (LN), ReLU] x (2 or 3), the first layer fused across the heads, then the tiny output layers.
+    // With LayerNorm the GEMM leaves fp32 pre-activations and the LN kernel applies LN+ReLU; without it ReLU rides the epilogue.
+    const int d2 = f.mlp_dim2;
+    const bool lnm = f.mlp_layernorm != 0;
+    const LnMap idm{0, 0, 0};
+    if (lnm) {
+      RET(gemm(c->head_in, H, Bm, c->w_mlp1, H, n, 2 * d0, H, c->mlp1, 2 * d0, 1, c->b_mlp1, ACT_NONE, nullptr, nullptr, 0, nd, 1));
+      RET(ln<float, T>(c->mlp1, d0, c->g_mlp1, c->be_mlp1, 2, d0, tp(c->y1), d0, idm, nullptr, 0, 1, 2 * n, nd, 2));
+    } else {
+      RET(gemm(c->head_in, H, Bm, c->w_mlp1, H, n, 2 * d0, H, c->y1, 2 * d0, 0, c->b_mlp1, ACT_RELU, nullptr, nullptr, 0, nd, 1));
+    }
+    const float* y_last = c->y2;
+    int d_last = d1;
+    {
+      const bool last = (d2 == 0);
+      void* dst = lnm ? static_cast<void*>(c->mlp2) : (last ? static_cast<void*>(c->y2) : c->y2t);
+      const int of32 = (lnm || last) ? 1 : 0;
+      const int esz = (of32 || c->dtype == 1) ? 4 : 2;
+      RET(gemm(c->y1, 2 * d0, Bm, c->w_mlp2_pose, d0, n, d1, d0, dst, 2 * d1, of32, c->b_mlp2, lnm ? ACT_NONE : ACT_RELU, nullptr, nullptr, 0, nd, 1));
+      RET(gemm(tp(c->y1) + d0, 2 * d0, Bm, c->w_mlp2_grip, d0, n, d1, d0, reinterpret_cast<char*>(dst) + (size_t)d1 * esz, 2 * d1, of32, c->b_mlp2 + d1,
+               lnm ? ACT_NONE : ACT_RELU, nullptr, nullptr, 0, nd, 1));
+      if (lnm) {
+        if (last) RET(ln<float, float>(c->mlp2, d1, c->g_mlp2, c->be_mlp2, 2, d1, c->y2, d1, idm, nullptr, 0, 1, 2 * n, nd, 2));
+        else RET(ln<float, T>(c->mlp2, d1, c->g_mlp2, c->be_mlp2, 2, d1, tp(c->y2t), d1, idm, nullptr, 0, 1, 2 * n, nd, 2));
+      }
+    }
+    if (d2 > 0) {
+      void* dst = lnm ? static_cast<void*>(c->mlp3) : static_cast<void*>(c->y3);
+      RET(gemm(c->y2t, 2 * d1, Bm, c->w_mlp3_pose, d1, n, d2, d1, dst, 2 * d2, 1, c->b_mlp3, lnm ? ACT_NONE : ACT_RELU, nullptr, nullptr, 0, nd, 1));
+      RET(gemm(tp(c->y2t) + d1, 2 * d1, Bm, c->w_mlp3_grip, d1, n, d2, d1, reinterpret_cast<float*>(dst) + d2, 2 * d2, 1, c->b_mlp3 + d2,
+               lnm ? ACT_NONE : ACT_RELU, nullptr, nullptr, 0, nd, 1));
+      if (lnm) RET(ln<float, float>(c->mlp3, d2, c->g_mlp3, c->be_mlp3, 2, d2, c->y3, d2, idm, nullptr, 0, 1, 2 * n, nd, 2));
+      y_last = c->y3; d_last = d2;
+    }
+    launch_k(head_out_kernel, dim3(n), dim3(256), 0, st, c->gemm.pdl, y_last, d_last, c->w3_pose, c->b3_pose, c->w3_grip, c->b3_grip, c->cur_pose, c->cur_grip, n, nd);
     KLAUNCH_CHECK("head_out");
     return DEER_OK;
   }
@@ -1080,7 +1160,7 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
   if (!delta_out) delta_out = c->o_delta;
   c->tap_n = n; c->tap_S = S;
   init_episodes_kernel<<<(n + 127) / 128, 128, 0, s.st>>>(c->meta[0], c->n_active, slots, ids, mask, timesteps, n, S, f.media_token_id,
-                                                          f.steps_per_stage, nthr_step, exit_out, delta_out);
+                                                          f.steps_per_stage, nthr_step, exit_out, delta_out, f.max_slots);
   KLAUNCH_CHECK("init_episodes");
   if (gen) CK(cudaMemsetAsync(c->pend_flag, 0, n, s.st));
   c->n_probes_last = 0; c->n_last = n;
@@ -1129,6 +1209,7 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
     g.cur_pose = c->cur_pose; g.cur_grip = c->cur_grip; g.cur_exit_id = c->cur_exit_id;
     g.pose_out = pose_out; g.grip_out = grip_out; g.action_out = action_out; g.exit_out = exit_out; g.delta_out = delta_out;
     g.exit_flag = c->exit_flag; g.src_of_new = c->src_of_new;
+    g.ensemble = (f.action_ensemble && static_exit < 0 && !gen) ? 1 : 0; g.probe_idx = c->n_probes_last;
     const int nxt = s.cur ^ 1;
     // graph capture: the layers after this exit go into a conditional IF node; the gate kernel sets its condition
     const bool wrap_cond = (c->cap_level >= 0) && !g.forced;
@@ -1159,11 +1240,12 @@ static int step_impl(deer_ctx* c, int n, const int32_t* slots, const float* rgb,
       continue;
     }
     commit_state_kernel<<<dim3(n, f.lstm_layers), 256, 0, s.st>>>(c->exit_flag, c->meta[s.cur].slot, c->cand_h, c->cand_c, c->h_state, c->c_state,
-                                                               f.lstm_layers, f.lstm_hidden, f.max_batch, n, c->n_active + s.cur);
+                                                               f.lstm_layers, f.lstm_hidden, f.max_batch, n, c->n_active + s.cur,
+                                                               c->meta[s.cur].orig, c->pooled, c->o_feat, f.d_model);
     KLAUNCH_CHECK("commit_state");
     if (g.forced) break;
     compact_kernel<T><<<dim3(n, 8), 256, 0, s.st>>>(c->src_of_new, c->x[s.cur], c->x[nxt], (size_t)S * f.d_model, s.tp(c->media[s.cur]), s.tp(c->media[nxt]),
-                                                  (size_t)2 * c->nl * f.vit_width, c->meta[s.cur], c->meta[nxt], c->cur_pose, S, n, c->n_active + nxt);
+                                                  (size_t)2 * c->nl * f.vit_width, c->meta[s.cur], c->meta[nxt], c->cur_pose, c->cur_grip, S, n, c->n_active + nxt);
     KLAUNCH_CHECK("compact");
     s.cur = nxt;
     if (wrap_cond) {
@@ -1202,8 +1284,8 @@ static int validate_step(deer_ctx* c, int n, int S, int static_exit, uint32_t fl
     return set_err(&c->err, DEER_E_STATE, "Please set thresholds before calling forward (value_net.py:279)");
   if (n < 1 || n > c->cfg.max_batch) return set_err(&c->err, DEER_E_INVALID, "n=%d outside [1,%d]", n, c->cfg.max_batch);
   if (S < 1 || S > c->cfg.max_seq) return set_err(&c->err, DEER_E_INVALID, "S=%d outside [1,%d]", S, c->cfg.max_seq);
-  if (static_exit >= c->cfg.n_layers || static_exit > c->ctrl_max_layer)
-    return set_err(&c->err, DEER_E_INVALID, "exit_id %d out of range (flamingo_mpt.py:449)", static_exit);
+  if (static_exit >= c->cfg.n_layers)
+    return set_err(&c->err, DEER_E_INVALID, "exit_id %d out of range [0, %d) (flamingo_mpt.py:449)", static_exit, c->cfg.n_layers);
   return DEER_OK;
 }
 
@@ -1330,6 +1412,7 @@ extern "C" int deer_step_host(deer_ctx* c, int n, const int32_t* slots, const fl
     if (slots[i] < 0 || slots[i] >= c->cfg.max_slots) return set_err(&c->err, DEER_E_INVALID, "slot %d out of range", slots[i]);
   cudaSetDevice(c->device);
   cudaStream_t st = c->own_stream;
+  order_after_last(c, st);        // a previous step (any stream) may still read the staging buffers
   const size_t img = (size_t)3 * c->cfg.image_size * c->cfg.image_size * 4;
   CK(cudaMemcpyAsync(c->s_rgb, rgb, n * img, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(c->s_grip, gripper, n * img, cudaMemcpyHostToDevice, st));
@@ -1356,6 +1439,38 @@ extern "C" int deer_get_state(deer_ctx* c, int slot, float* h_out, float* c_out)
   CK(cudaDeviceSynchronize());
   if (h_out) CK(cudaMemcpy(h_out, reinterpret_cast<char*>(c->h_state) + per * slot, per, cudaMemcpyDeviceToHost));
   if (c_out) CK(cudaMemcpy(c_out, reinterpret_cast<char*>(c->c_state) + per * slot, per, cudaMemcpyDeviceToHost));
+  return DEER_OK;
+}
+
+extern "C" int deer_set_state(deer_ctx* c, int slot, const float* h, const float* cc) {
+  if (!c) return set_err(nullptr, DEER_E_INVALID, "null ctx");
+  if (slot < 0 || slot >= c->cfg.max_slots) return set_err(&c->err, DEER_E_INVALID, "slot out of range");
+  if (!h || !cc) return set_err(&c->err, DEER_E_INVALID, "null state pointer");
+  cudaSetDevice(c->device);
+  const size_t per = (size_t)c->cfg.lstm_layers * c->cfg.lstm_hidden * 4;
+  cudaStream_t st = c->has_last ? c->last_stream : c->own_stream;
+  CK(cudaMemcpyAsync(reinterpret_cast<char*>(c->h_state) + per * slot, h, per, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(reinterpret_cast<char*>(c->c_state) + per * slot, cc, per, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));                 // the host buffers may be pageable / freed by the caller right away
+  mark_done(c, st);
+  return DEER_OK;
+}
+
+extern "C" int deer_get_features(deer_ctx* c, int n, float* out, int out_is_host, void* stream) {
+  if (!c || !out) return set_err(c ? &c->err : nullptr, DEER_E_INVALID, "null argument");
+  if (n < 1 || n > c->n_last) return set_err(&c->err, DEER_E_INVALID, "n=%d but the last step had %d episodes", n, c->n_last);
+  cudaSetDevice(c->device);
+  const size_t bytes = (size_t)n * c->cfg.d_model * 4;
+  if (out_is_host) {
+    cudaStream_t st = c->has_last ? c->last_stream : c->own_stream;
+    CK(cudaMemcpyAsync(out, c->o_feat, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  } else {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    order_after_last(c, st);
+    CK(cudaMemcpyAsync(out, c->o_feat, bytes, cudaMemcpyDeviceToDevice, st));
+    mark_done(c, st);
+  }
   return DEER_OK;
 }
 
@@ -1414,6 +1529,8 @@ extern "C" int deer_get_profile(deer_ctx* c, deer_profile* out) {
     }
     out->gemm_ms[r.tag] += ms;
     out->gemm_flops[r.tag] += 2.0 * M * r.n * r.k;
+    // algorithmic HBM bytes: A and W read once, C written once, fp32 residual read once
+    out->gemm_bytes[r.tag] += ((double)M * r.k + (double)r.n * r.k) * r.in_es + (double)M * r.n * (r.out_es + (r.has_res ? 4 : 0));
     out->gemm_launches[r.tag]++;
   }
   if (c->ev_step0 && c->gemm.profile) {
@@ -1587,6 +1704,7 @@ extern "C" int deer_step_host_u8(deer_ctx* c, int n, const int32_t* slots, const
       CK(cudaMalloc(reinterpret_cast<void**>(&c->u8_stage[k]), cap));
       c->u8_cap[k] = cap;
     }
+  order_after_last(c, st);        // a previous step (any stream) may still read the staging buffers
   CK(cudaMemcpyAsync(c->u8_stage[0], rgb, bytes[0], cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(c->u8_stage[1], gripper, bytes[1], cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(c->s_ids, ids, (size_t)n * S * 8, cudaMemcpyHostToDevice, st));

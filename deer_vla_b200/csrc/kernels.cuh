@@ -229,17 +229,20 @@ struct EpisodeMeta {          // all arrays sized max_batch; "r" = rank inside t
   int* valid_len;             // r -> number of real tokens
   uint8_t* xmode;             // [r, S] x-attn class per token (0 no media yet, 1 attend, 2 more than one <image>)
   float* prev_pose;           // [r, 6] previous exit's pose
+  float* prev_grip;           // [r] previous exit's gripper output (action ensemble, value_net.py:92-95)
   uint8_t* use_prev;          // r -> 1 when timestep % steps_per_stage != 0 (reuse cur_exit_id, value_net.py:285)
 };
 
 __global__ void init_episodes_kernel(EpisodeMeta m, int* n_active, const int* __restrict__ slots, const int64_t* __restrict__ ids,
                                      const uint8_t* __restrict__ mask, const int* __restrict__ timesteps, int n, int S,
-                                     int media_id, int sps, int n_thr, int* __restrict__ exit_dev, float* __restrict__ delta_dev) {
+                                     int media_id, int sps, int n_thr, int* __restrict__ exit_dev, float* __restrict__ delta_dev,
+                                     int max_slots) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r == 0) *n_active = n;
   if (r >= n) return;
   m.orig[r] = r;
-  m.slot[r] = slots[r];
+  const int sl = slots[r];                     // device-resident slot ids cannot be validated on the host: never index out of bounds
+  m.slot[r] = sl < 0 ? 0 : (sl >= max_slots ? max_slots - 1 : sl);
   int vl = 0, tt = 0;
   for (int s = 0; s < S; ++s) {
     vl += mask[r * S + s] ? 1 : 0;
@@ -330,6 +333,14 @@ lstm_cell_kernel(const float* __restrict__ gates, const float* __restrict__ c_st
     hv[it] = h2;
     s += h2;
   }
+  if (gamma == nullptr) {                      // plain stacked nn.LSTM (lstm_layernorm=False): the next layer sees h itself
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int j = threadIdx.x + it * 256;
+      if (j < Hh) y[static_cast<size_t>(r) * y_ld + j] = from_f32<T>(hv[it]);
+    }
+    return;
+  }
   const float mean = block_sum(s, red) / Hh;
   float q = 0.0f;
 #pragma unroll
@@ -396,6 +407,9 @@ struct GateParams {
   // CUDA-graph control flow: when has_cond, the conditional IF node that wraps every later layer runs iff survivors remain
   cudaGraphConditionalHandle cond;
   int has_cond;
+  // action ensemble (eval_utils.py:457-462): action_out = mean of the last two entries of this step's action_list
+  int ensemble;
+  int probe_idx;             // probes evaluated before this one in the step (= len(action_list) before the append)
 };
 
 __global__ void __launch_bounds__(1024)
@@ -432,7 +446,7 @@ exit_gate_kernel(GateParams g, EpisodeMeta m, const int* __restrict__ n_cur, int
       ex = g.forced != 0;
       if (g.exit_idx >= 0 && g.delta_out) g.delta_out[o * g.n_thr + g.exit_idx] = delta;
     } else if (m.use_prev[r]) {
-      ex = g.layer >= g.cur_exit_id[sl];                            // value_net.py:285-286
+      ex = g.forced || g.layer >= g.cur_exit_id[sl];                // value_net.py:285-286
     } else {
       if (g.exit_idx >= 0 && g.has_prev && g.delta_out) g.delta_out[o * g.n_thr + g.exit_idx] = delta;
       const bool leq = (g.exit_idx >= 0 && g.has_prev) ? (delta <= g.thresholds[g.exit_idx]) : false;
@@ -444,8 +458,11 @@ exit_gate_kernel(GateParams g, EpisodeMeta m, const int* __restrict__ n_cur, int
       if (g.pose_out) for (int k = 0; k < 6; ++k) g.pose_out[o * 6 + k] = cp[k];
       if (g.grip_out) g.grip_out[o] = gr;
       if (g.action_out) {                                           // eval_utils.py:458,464
-        for (int k = 0; k < 6; ++k) g.action_out[o * 7 + k] = cp[k];
-        g.action_out[o * 7 + 6] = (gr > 0.5f) ? 1.0f : -1.0f;
+        // ensemble: torch.stack(action_list[-2:]).mean(0) -- one entry only when this is the step's first probe
+        const bool ens = g.ensemble && g.probe_idx > 0 && g.has_prev && !m.use_prev[r];
+        const float ga = ens ? (gr + m.prev_grip[r]) / 2.0f : gr;
+        for (int k = 0; k < 6; ++k) g.action_out[o * 7 + k] = ens ? (cp[k] + m.prev_pose[r * 6 + k]) / 2.0f : cp[k];
+        g.action_out[o * 7 + 6] = (ga > 0.5f) ? 1.0f : -1.0f;
       }
       if (g.exit_out) g.exit_out[o] = g.layer;
     }
@@ -492,7 +509,8 @@ exit_gate_kernel(GateParams g, EpisodeMeta m, const int* __restrict__ n_cur, int
 // commit the candidate LSTM state of the episodes that exit now (update_hidden_state=True, action_head.py:554-556)
 __global__ void commit_state_kernel(const uint8_t* __restrict__ exit_flag, const int* __restrict__ slot, const float* __restrict__ cand_h,
                                     const float* __restrict__ cand_c, float* __restrict__ h_state, float* __restrict__ c_state,
-                                    int layers, int Hh, int nstride, int n_host, const int* __restrict__ n_dev) {
+                                    int layers, int Hh, int nstride, int n_host, const int* __restrict__ n_dev,
+                                    const int* __restrict__ orig, const float* __restrict__ pooled, float* __restrict__ feat_out, int D) {
   const int n = dyn_rows(n_host, n_dev, 1);
   const int r = blockIdx.x, l = blockIdx.y;
   if (r >= n || !exit_flag[r]) return;
@@ -501,6 +519,11 @@ __global__ void commit_state_kernel(const uint8_t* __restrict__ exit_flag, const
   for (int j = threadIdx.x; j < Hh; j += blockDim.x) {
     h_state[dst + j] = cand_h[src + j];
     c_state[dst + j] = cand_c[src + j];
+  }
+  if (l == 0 && feat_out != nullptr) {         // `.logits[2]`: the pooled feature of the exit layer (action_head.py:608-609)
+    const float* ps = pooled + static_cast<size_t>(r) * D;
+    float* fo = feat_out + static_cast<size_t>(orig[r]) * D;
+    for (int j = threadIdx.x; j < D; j += blockDim.x) fo[j] = ps[j];
   }
 }
 
@@ -529,7 +552,7 @@ __global__ void commit_pending_kernel(const uint8_t* __restrict__ pend_flag, con
 template <typename T>
 __global__ void compact_kernel(const int* __restrict__ src_of_new, const float* __restrict__ x_in, float* __restrict__ x_out, size_t x_per,
                                const T* __restrict__ media_in, T* __restrict__ media_out, size_t media_per,
-                               EpisodeMeta mi, EpisodeMeta mo, const float* __restrict__ cur_pose, int S,
+                               EpisodeMeta mi, EpisodeMeta mo, const float* __restrict__ cur_pose, const float* __restrict__ cur_grip, int S,
                                int n_host, const int* __restrict__ n_next) {
   const int n = dyn_rows(n_host, n_next, 1);
   const int r2 = blockIdx.x;
@@ -548,6 +571,7 @@ __global__ void compact_kernel(const int* __restrict__ src_of_new, const float* 
       mo.slot[r2] = mi.slot[r];
       mo.valid_len[r2] = mi.valid_len[r];
       mo.use_prev[r2] = mi.use_prev[r];
+      mo.prev_grip[r2] = cur_grip[r];
     }
     if (threadIdx.x < 6) mo.prev_pose[r2 * 6 + threadIdx.x] = cur_pose[r * 6 + threadIdx.x];   // action_list[-1], value_net.py:127
     for (int s = threadIdx.x; s < S; s += blockDim.x) mo.xmode[r2 * S + s] = mi.xmode[r * S + s];

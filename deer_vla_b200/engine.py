@@ -27,16 +27,16 @@ class DeerEngine:
 
     def __init__(self, cfg: DeerConfig, max_batch: int = 1, max_slots: Optional[int] = None, max_seq: int = 32,
                  device: int = 0, precision: str = "bf16", gemm_impl: str = "tcgen05", debug_taps: bool = False,
-                 host_control: bool = False, use_graph: bool = False):
+                 host_control: bool = False, use_graph: bool = False, action_ensemble: bool = False):
         self.lib = _lib.load()
         self.cfg = cfg
         self.device = torch.device("cuda", device)
         self.max_batch = int(max_batch)
         self.max_slots = int(max_slots if max_slots is not None else max_batch)
         self.max_seq = int(max_seq)
-        if len(cfg.mlp_dims) != 2:
-            raise ValueError("the engine implements the trained head config mlp_num_hidden_layers=2 "
-                             "(train_calvin_post_strategy.py:343-344)")
+        if len(cfg.mlp_dims) not in (2, 3):
+            raise ValueError("mlp_num_hidden_layers must be 2 (the trained DeeR head, train_calvin_post_strategy.py:343-344) "
+                             "or 3 (older checkpoints, eval_calvin.py:473)")
         cc = DeerCConfig()
         cc.abi_version = _lib.ABI_VERSION
         for k in ("image_size", "patch", "vit_width", "vit_layers", "vit_heads", "vit_mlp", "perc_depth", "perc_heads",
@@ -48,6 +48,9 @@ class DeerEngine:
         cc.n_layers = cfg.n_layers
         cc.is_mpt_9b = int("mpt_9b" in cfg.llm_name)
         cc.mlp_dim0, cc.mlp_dim1 = int(cfg.mlp_dims[0]), int(cfg.mlp_dims[1])
+        cc.mlp_dim2 = int(cfg.mlp_dims[2]) if len(cfg.mlp_dims) == 3 else 0
+        cc.mlp_layernorm, cc.lstm_layernorm = int(bool(cfg.mlp_layernorm)), int(bool(cfg.lstm_layernorm))
+        cc.action_ensemble = int(bool(action_ensemble))
         cc.threshold_type = _lib.THR_TYPES[cfg.threshold_type]
         cc.max_batch, cc.max_slots, cc.max_seq = self.max_batch, self.max_slots, self.max_seq
         cc.precision = {"bf16": _lib.PREC_BF16, "fp32": _lib.PREC_FP32}[precision]
@@ -56,6 +59,8 @@ class DeerEngine:
         cc.host_control = int(host_control)
         cc.use_graph = int(use_graph)
         self.precision = precision
+        self.action_ensemble = bool(action_ensemble)
+        self.debug_taps = bool(debug_taps)
         self._h = C.c_void_p()
         rc = self.lib.deer_create(C.byref(cc), device, C.byref(self._h))
         if rc != 0:
@@ -115,6 +120,7 @@ class DeerEngine:
         stages = ("vit", "perceiver", "llm", "head")
         return {"gemm_ms": {s: p.gemm_ms[i] for i, s in enumerate(stages)},
                 "gemm_flops": {s: p.gemm_flops[i] for i, s in enumerate(stages)},
+                "gemm_bytes": {s: p.gemm_bytes[i] for i, s in enumerate(stages)},
                 "gemm_launches": {s: int(p.gemm_launches[i]) for i, s in enumerate(stages)},
                 "step_ms": p.step_ms, "active_after": [int(p.active_after[i]) for i in range(p.n_probes)]}
 
@@ -277,6 +283,25 @@ class DeerEngine:
         dims = [int(s) for s in shape if s > 0]
         n = int(np.prod(dims))
         return buf[:n].reshape(dims).copy()
+
+    def set_state(self, slot: int, h: np.ndarray, c: np.ndarray):
+        """Overwrite one slot's carried LSTM state -- `model.extra_exit.hidden_state = (h, c)` (action_head.py:474,554-558)."""
+        shp = (self.cfg.lstm_layers, self.cfg.lstm_hidden)
+        h = np.ascontiguousarray(h, dtype=np.float32).reshape(shp)
+        c = np.ascontiguousarray(c, dtype=np.float32).reshape(shp)
+        self._check(self.lib.deer_set_state(self._h, slot, h.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p)))
+
+    def features(self, n: int, device: bool = True) -> torch.Tensor:
+        """`.logits[2]` of the last step: (n, d_model) max-pooled token feature each episode's exit head consumed
+        (action_head.py:519-520,608-609), as a CUDA tensor (stream-ordered copy) or a host tensor."""
+        if device:
+            out = torch.empty(n, self.cfg.d_model, dtype=torch.float32, device=self.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self._check(self.lib.deer_get_features(self._h, n, _ptr(out), 0, C.c_void_p(stream)))
+        else:
+            out = torch.empty(n, self.cfg.d_model, dtype=torch.float32)
+            self._check(self.lib.deer_get_features(self._h, n, _ptr(out), 1, None))
+        return out
 
     def get_state(self, slot: int):
         shp = (self.cfg.lstm_layers, self.cfg.lstm_hidden)

@@ -75,8 +75,15 @@ def postprocess_action(pose: torch.Tensor, gripper: torch.Tensor, multi_executio
 class ModelWrapper:
     def __init__(self, model, tokenizer, image_processor, cast_dtype=None, use_diff=False, history_len=None, future_act_len=-1,
                  amp=False, exit_id=None, early_exit=False, exit_controller=None, multi_execution=1, use_action_ensemble=False):
-        assert not use_diff and not use_action_ensemble, "deterministic LSTM head only (eval_calvin.py:201,315)"
+        assert not use_diff, "deterministic LSTM head only (eval_calvin.py:201)"
         self.model = model
+        self.use_action_ensemble = use_action_ensemble
+        if use_action_ensemble:
+            # the mean over the last two probes' actions is taken inside the exit gate (deer_config.action_ensemble);
+            # the reference's get_ensemble_action needs a probe this step, i.e. the dynamic path (value_net.py:92-95)
+            assert model.module.engine.action_ensemble, "build the engine with action_ensemble=True (factory: use_action_ensemble)"
+            assert early_exit and exit_controller is not None, "use_action_ensemble needs dynamic early exit (value_net.py:93)"
+            assert int(model.module.cfg.steps_per_stage) == 1, "action_list is empty on non-boundary steps (value_net.py:285-286,93)"
         self.replan = model.module.replan
         self.decoder_type = model.module.decoder_type
         self.head_type = model.module.head_type
@@ -105,9 +112,24 @@ class ModelWrapper:
                          vision_gripper=gripper.to(self.device), state_tensor=None, return_feature=True, deterministic=True,
                          exit_id=self.exit_id, dynamic_early_exit=self.dynamic_early_exit, exit_controller=self.exit_controller)
         self.current_exit_layer = out.exit_layer
-        action = postprocess_action(out.logits[0], out.logits[1], self.multi_execution)
+        if self.use_action_ensemble:                                    # eval_utils.py:460-464: mean of action_list[-2:], gripper > 0.5, +-1
+            a = out.action.reshape(-1, 7)[-1]
+            action = torch.stack([a] * self.multi_execution, dim=0).cpu().detach().to(dtype=torch.float16).numpy()
+        else:
+            action = postprocess_action(out.logits[0], out.logits[1], self.multi_execution)
         self.model.module.set_all_exit_window_size(window_size)
         return action
+
+    def on_rollout_step(self, step: int):
+        """The per-step bookkeeping of the reference's rollout loop (eval_utils.py:652-663): every ``replan`` steps the policy
+        is reset (``refresh == -1``); with ``refresh != -1`` the reference only clears ``lang_encoder.lm_head`` and trims the
+        value net's history, neither of which the DeeR exit head reads, so the carried LSTM state is kept.  Then
+        ``exit_controller.set_timestep(step)``."""
+        m = self.model.module
+        if self.replan != -1 and step % self.replan == 0 and m.refresh == -1:
+            self.reset()
+        if self.exit_controller is not None:
+            self.exit_controller.module.set_timestep(step)
 
 
 class BatchedModelWrapper:

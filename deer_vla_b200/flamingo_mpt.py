@@ -35,7 +35,12 @@ class _HeadState:
             self._owner.engine.reset()
             self._owner._state_marker = None
         else:
-            raise NotImplementedError("the LSTM state is owned by the engine; only clearing (None) is supported")
+            # (h, c) each (layers, B, hidden) like nn.LSTM's state (action_head.py:554-558): written into slots 0..B-1
+            h, c = v
+            h, c = torch.as_tensor(h).detach().float().cpu().numpy(), torch.as_tensor(c).detach().float().cpu().numpy()
+            for b in range(h.shape[1]):
+                self._owner.engine.set_state(b, h[:, b], c[:, b])
+            self._owner._state_marker = "engine"
 
 
 class MPTFlamingo:
@@ -46,6 +51,8 @@ class MPTFlamingo:
             "the engine implements the DeeR evaluation configuration (eval_calvin.py:173-177; SURVEY App. A-12)"
         self.engine, self.cfg = engine, cfg
         self.window_size, self.pad_length, self.replan, self.refresh = window_size, pad_length, replan, refresh
+        if self.replan != -1:                              # flamingo_mpt.py:102-104
+            self.replan = min(int(replan * self.window_size), 180)
         self.use_gripper, self.use_state, self.fusion_mode = use_gripper, use_state, fusion_mode
         self.decoder_type, self.head_type = "lstm", "deterministic"
         self.sep_lm_head, self.act_step, self.tcp_rel = True, multi_step_action, tcp_rel
@@ -117,9 +124,17 @@ class MPTFlamingo:
                                lang_x, attention_mask, slots=slots, timesteps=timesteps, exit_id=static_exit)
         self._state_marker = "engine"
         exit_layer = out["exit_layer"]
+        # .logits[2]: the pooled feature the exit head consumed (return_feature=True, flamingo_mpt.py:458-460)
+        feat = self.engine.features(B, device=vision_x.is_cuda) if return_feature else None
+        # .hidden_states (opt-in: engine built with debug_taps): tuple of (B, S, d) post-block states of layers 0..exit
+        # (mosaic_gpt_3b.py:424-427); rows of episodes that left earlier keep the state they left with
+        hidden = None
+        if self.engine.debug_taps:
+            last = int(exit_layer.max())
+            hidden = tuple(torch.from_numpy(self.engine.get_tap("hidden", l)) for l in range(last + 1))
         return SimpleNamespace(
-            logits=(out["pose"].view(B, 1, 6), out["gripper"].view(B, 1, 1), None),
+            logits=(out["pose"].view(B, 1, 6), out["gripper"].view(B, 1, 1), feat),
             exit_layer=int(exit_layer[0]) if B == 1 else exit_layer,
-            exit_layers=exit_layer, action=out["action"], delta=out["delta"], hidden_states=None, past_key_values=None)
+            exit_layers=exit_layer, action=out["action"], delta=out["delta"], hidden_states=hidden, past_key_values=None)
 
     __call__ = forward

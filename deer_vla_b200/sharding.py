@@ -48,6 +48,9 @@ def all_gather_values(values: torch.Tensor) -> torch.Tensor:
     (n_exit, n_total) on every rank."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
         return values
-    bufs = [torch.zeros_like(values) for _ in range(dist.get_world_size())]
-    dist.all_gather(bufs, values.contiguous())
-    return torch.cat(bufs, dim=1)
+    src = values.contiguous()
+    if dist.get_backend() == "nccl" and not src.is_cuda:       # NCCL moves device tensors only
+        src = src.cuda()
+    bufs = [torch.zeros_like(src) for _ in range(dist.get_world_size())]
+    dist.all_gather(bufs, src)
+    return torch.cat(bufs, dim=1).to(values.device)

@@ -74,7 +74,9 @@ class ExitController:
         self.exit_dist = exit_dist
         self.max_layer = min(max_layer - 1, self.exit_id_list[-1])
         self.cur_step = 0
-        self.engine = engine
+        self.engine = None
+        if engine is not None:
+            self.attach(engine)
 
     @property
     def module(self):          # the reference wraps the controller in DDP and reaches through .module (eval_calvin.py:590)
@@ -84,6 +86,15 @@ class ExitController:
         return self
 
     def attach(self, engine):
+        """Bind to an engine.  The gate runs inside the engine with the ENGINE's exit bookkeeping, so a controller built with
+        different options would silently be ignored: refuse instead (value_net.py:163-173,285-286)."""
+        ecfg = engine.cfg
+        if list(engine.exit_list) != list(self.exit_id_list):
+            raise ValueError(f"exit_id_list {self.exit_id_list} != the engine's exit list {engine.exit_list} (flamingo_mpt.py:268-270)")
+        if ecfg.ctrl_max_layer != self.max_layer:
+            raise ValueError(f"controller max_layer {self.max_layer} != engine {ecfg.ctrl_max_layer} (value_net.py:173)")
+        if int(ecfg.steps_per_stage) != int(self.steps_per_stage):
+            raise ValueError(f"controller steps_per_stage {self.steps_per_stage} != engine {ecfg.steps_per_stage} (value_net.py:285)")
         self.engine = engine
         if self.thresholds is not None:
             engine.set_thresholds([self.thresholds[e] for e in self._real_exits()])
@@ -104,6 +115,9 @@ class ExitController:
         ``generate_action_values`` (value_net.py:300-399)."""
         if values is None:
             values = generate_action_values(self.engine if self.engine is not None else model, dataloader)
+            # every rank calibrates on its own shard; the solver sees all of them (value_net.py:192-201)
+            from .sharding import all_gather_values
+            values = all_gather_values(torch.as_tensor(values))
         real = self._real_exits()
         values = torch.as_tensor(values)[: len(real)]
         T = solve_thresholds(values, exit_ratio, self.exit_dist, model_name, self.leq)

@@ -71,17 +71,23 @@ def state_dict_spec(cfg: DeerConfig) -> List[Spec]:
                   (p + "ffn.up_proj.weight", (cfg.mlp_ratio * D, D), "w"), (p + "ffn.down_proj.weight", (D, cfg.mlp_ratio * D), "w")]
     H = cfg.lstm_hidden
     for l in range(cfg.lstm_layers):
-        p = f"extra_exit.rnn.layers.{3 * l}."
         ins = D if l == 0 else H
-        s += [(p + "weight_ih_l0", (4 * H, ins), "lstm"), (p + "weight_hh_l0", (4 * H, H), "lstm"),
-              (p + "bias_ih_l0", (4 * H,), "lstm"), (p + "bias_hh_l0", (4 * H,), "lstm"),
-              (f"extra_exit.rnn.layers.{3 * l + 1}.weight", (H,), "g"), (f"extra_exit.rnn.layers.{3 * l + 1}.bias", (H,), "be")]
+        if cfg.lstm_layernorm:                     # LayerNormLSTM (action_head.py:15-40)
+            p = f"extra_exit.rnn.layers.{3 * l}."
+            s += [(p + "weight_ih_l0", (4 * H, ins), "lstm"), (p + "weight_hh_l0", (4 * H, H), "lstm"),
+                  (p + "bias_ih_l0", (4 * H,), "lstm"), (p + "bias_hh_l0", (4 * H,), "lstm"),
+                  (f"extra_exit.rnn.layers.{3 * l + 1}.weight", (H,), "g"), (f"extra_exit.rnn.layers.{3 * l + 1}.bias", (H,), "be")]
+        else:                                      # stacked nn.LSTM (action_head.py:71-79)
+            p = "extra_exit.rnn."
+            s += [(p + f"weight_ih_l{l}", (4 * H, ins), "lstm"), (p + f"weight_hh_l{l}", (4 * H, H), "lstm"),
+                  (p + f"bias_ih_l{l}", (4 * H,), "lstm"), (p + f"bias_hh_l{l}", (4 * H,), "lstm")]
     for head, out in (("actions", 6), ("gripper", 1)):
         cur = H
-        for j, dim in enumerate(cfg.mlp_dims):
+        for j, dim in enumerate(cfg.mlp_dims):     # canonical 'layerwise' Sequential indices (checkpoint.canonical_head_keys)
             p = f"extra_exit.{head}.mlp."
-            s += [(p + f"{4 * j + 1}.weight", (dim, cur), "w"), (p + f"{4 * j + 1}.bias", (dim,), "b"),
-                  (p + f"{4 * j + 2}.weight", (dim,), "g"), (p + f"{4 * j + 2}.bias", (dim,), "be")]
+            s += [(p + f"{4 * j + 1}.weight", (dim, cur), "w"), (p + f"{4 * j + 1}.bias", (dim,), "b")]
+            if cfg.mlp_layernorm:
+                s += [(p + f"{4 * j + 2}.weight", (dim,), "g"), (p + f"{4 * j + 2}.bias", (dim,), "be")]
             cur = dim
         k = 4 * len(cfg.mlp_dims) + 1
         s += [(f"extra_exit.{head}.mlp.{k}.weight", (out, cur), "wout"), (f"extra_exit.{head}.mlp.{k}.bias", (out,), "b")]

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DEER_ABI_VERSION 1
+#define DEER_ABI_VERSION 2   /* 2: deer_config grew mlp_dim2 / mlp_layernorm / lstm_layernorm / action_ensemble */
 
 enum {
   DEER_OK = 0,
@@ -87,6 +87,14 @@ typedef struct deer_config {
                                 post-exit segments are nested conditional IF nodes; exit_gate_kernel sets the condition
                                 (cudaGraphSetConditional) from the device-side active count, so the layers past the
                                 last active episode's exit are never launched and no host round trip is needed */
+  /* head variants of older DeeR checkpoints (eval_calvin.py:464-476; action_head.py:66-79, 82-161): the trained DeeR
+   * configuration is mlp_dim2 = 0 (two hidden layers), mlp_layernorm = lstm_layernorm = 1 */
+  int32_t mlp_dim2;          /* > 0: a third hidden layer of this width (mlp_num_hidden_layers=3: 1024, 512, 256) */
+  int32_t mlp_layernorm;     /* LayerNorm after every hidden Linear of both MLP heads */
+  int32_t lstm_layernorm;    /* 1: LayerNormLSTM (stored h pre-LN, next layer's input post-LN); 0: plain stacked nn.LSTM */
+  int32_t action_ensemble;   /* 1: action_out = mean of the exit's and the previous exit's (pose, gripper) -- ModelWrapper's
+                                use_action_ensemble (eval_utils.py:457-462, value_net.py:92-95); pose_out / gripper_out
+                                stay the exit head's own outputs */
 } deer_config;
 
 typedef struct deer_stats {
@@ -101,7 +109,9 @@ typedef struct deer_stats {
 
 /* library-level */
 int         deer_abi_version(void);
-const char* deer_build_info(void);            /* arch, compiler, flags */
+const char* deer_build_info(void);            /* arch, compiler, flags, "src=<hash>" */
+const char* deer_source_hash(void);           /* sha256 (hex) over csrc/ and include/ the library was built from; the binding
+                                                  refuses a library whose hash differs from the sources beside it */
 const char* deer_last_error(deer_ctx* ctx);   /* ctx may be NULL (creation errors) */
 
 /* lifetime  -- replaces create_model_and_transforms + model.to(device) (factory.py:53, eval_calvin.py:565) */
@@ -168,6 +178,7 @@ typedef struct deer_profile {
   double  step_ms;            /* device time of the whole last step (first to last kernel) */
   int32_t n_probes;           /* exits evaluated in the last step */
   int32_t active_after[16];   /* still-active episodes after each probe */
+  double  gemm_bytes[4];      /* algorithmic HBM bytes of those launches: A + W read once, C written once, fp32 residual read once */
 } deer_profile;
 int deer_set_profile(deer_ctx* ctx, int enable);
 int deer_get_profile(deer_ctx* ctx, deer_profile* out);
@@ -203,6 +214,14 @@ int deer_step_host_u8(deer_ctx* ctx, int n, const int32_t* slots, const uint8_t*
 
 /* introspection for parity tests (the reference exposes .hidden_states / module attributes) */
 int deer_get_state(deer_ctx* ctx, int slot, float* h_out, float* c_out);   /* HOST [layers, hidden] each */
+/* replaces assigning `model.extra_exit.hidden_state = (h, c)` (action_head.py:474,554-558): overwrite one slot's carried
+ * LSTM state.  HOST pointers [layers, hidden]; ordered after the last step like deer_reset. */
+int deer_set_state(deer_ctx* ctx, int slot, const float* h, const float* c);
+/* `.logits[2]` of the reference's output (return_feature=True: the max-pooled token feature the exit head consumed,
+ * action_head.py:519-520,608-609; flamingo_mpt.py:458-460) for the n episodes of the LAST step, row i = episode i of that
+ * call, taken at each episode's own exit layer.  out: [n, d_model] fp32, DEVICE (copied on `stream`) or HOST
+ * (out_is_host = 1; synchronises). */
+int deer_get_features(deer_ctx* ctx, int n, float* out, int out_is_host, void* stream);
 /* name: "vit" [2n, patches, width] (rgb images then gripper images), "media" [n, 2*latents, width],
  * "hidden" [n, S, d] (layer = LLM layer index; rows of episodes that exited earlier keep their last value),
  * "pooled" [n, d].  Requires cfg.debug_taps.  out is a HOST buffer of `capacity` floats; shape_out[4]. */

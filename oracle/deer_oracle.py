@@ -108,6 +108,9 @@ class DeerConfig:
     mlp_dims: Tuple[int, ...] = (1024, 512)
     threshold_type: str = "L2"
     steps_per_stage: int = 1
+    # head variants of older checkpoints (eval_calvin.py:464-476): mlp_dims (1024, 512, 256), no LayerNorms
+    mlp_layernorm: bool = True
+    lstm_layernorm: bool = True
 
     # ---- derived quantities -------------------------------------------------------
     @property
@@ -233,18 +236,24 @@ def weight_specs(cfg: DeerConfig) -> List[Tuple[str, Tuple[int, ...], str]]:
                   (p + "ffn.down_proj.weight", (D, cfg.mlp_ratio * D), "w")]
     H = cfg.lstm_hidden
     for l in range(cfg.lstm_layers):
-        p = f"extra_exit.rnn.layers.{3 * l}."      # action_head.py:23-39: [LSTM, LN, Dropout] * n
         ins = D if l == 0 else H
-        s += [(p + "weight_ih_l0", (4 * H, ins), "lstm"), (p + "weight_hh_l0", (4 * H, H), "lstm"),
-              (p + "bias_ih_l0", (4 * H,), "lstm"), (p + "bias_hh_l0", (4 * H,), "lstm"),
-              (f"extra_exit.rnn.layers.{3 * l + 1}.weight", (H,), "g"),
-              (f"extra_exit.rnn.layers.{3 * l + 1}.bias", (H,), "be")]
+        if cfg.lstm_layernorm:
+            p = f"extra_exit.rnn.layers.{3 * l}."      # action_head.py:23-39: [LSTM, LN, Dropout] * n
+            s += [(p + "weight_ih_l0", (4 * H, ins), "lstm"), (p + "weight_hh_l0", (4 * H, H), "lstm"),
+                  (p + "bias_ih_l0", (4 * H,), "lstm"), (p + "bias_hh_l0", (4 * H,), "lstm"),
+                  (f"extra_exit.rnn.layers.{3 * l + 1}.weight", (H,), "g"),
+                  (f"extra_exit.rnn.layers.{3 * l + 1}.bias", (H,), "be")]
+        else:                                          # action_head.py:71-79: one stacked nn.LSTM
+            p = "extra_exit.rnn."
+            s += [(p + f"weight_ih_l{l}", (4 * H, ins), "lstm"), (p + f"weight_hh_l{l}", (4 * H, H), "lstm"),
+                  (p + f"bias_ih_l{l}", (4 * H,), "lstm"), (p + f"bias_hh_l{l}", (4 * H,), "lstm")]
     for head, out in (("actions", 6), ("gripper", 1)):
         cur = H
-        for j, dim in enumerate(cfg.mlp_dims):     # action_head.py:96-108 (Sequential indices 1,2 / 5,6)
+        for j, dim in enumerate(cfg.mlp_dims):     # action_head.py:96-108 ('layerwise' Sequential indices 1,2 / 5,6 / 9,10)
             p = f"extra_exit.{head}.mlp."
-            s += [(p + f"{4 * j + 1}.weight", (dim, cur), "w"), (p + f"{4 * j + 1}.bias", (dim,), "b"),
-                  (p + f"{4 * j + 2}.weight", (dim,), "g"), (p + f"{4 * j + 2}.bias", (dim,), "be")]
+            s += [(p + f"{4 * j + 1}.weight", (dim, cur), "w"), (p + f"{4 * j + 1}.bias", (dim,), "b")]
+            if cfg.mlp_layernorm:
+                s += [(p + f"{4 * j + 2}.weight", (dim,), "g"), (p + f"{4 * j + 2}.bias", (dim,), "be")]
             cur = dim
         k = 4 * len(cfg.mlp_dims) + 1
         s += [(f"extra_exit.{head}.mlp.{k}.weight", (out, cur), "wout"),
@@ -283,6 +292,19 @@ def synth_weights(cfg: DeerConfig, seed: int = 0) -> Dict[str, Tensor]:
             raise ValueError(kind)
         out[name] = t.float().contiguous()
     return out
+
+
+def synth_weights_variant(cfg: DeerConfig, seed: int = 0) -> Dict[str, Tensor]:
+    """``synth_weights`` for the head variants WITHOUT LayerNorms (old checkpoints): with N(0, 0.02) / U(+-1/32) weights and
+    no normalisation the un-trained head is nearly constant (deltas ~1e-6, every exit decision would sit inside fp32 noise),
+    so the LSTM weights are scaled x6 and the MLP weights x3 where the corresponding LayerNorm is absent (deltas ~0.1)."""
+    W = synth_weights(cfg, seed)
+    for k in W:
+        if not cfg.lstm_layernorm and k.startswith("extra_exit.rnn.weight"):
+            W[k] = W[k] * 6.0
+        if not cfg.mlp_layernorm and ".mlp." in k and k.endswith("weight"):
+            W[k] = W[k] * 3.0
+    return W
 
 
 # --------------------------------------------------------------------------------------
@@ -526,19 +548,27 @@ def head_forward(cfg: DeerConfig, W: Dict[str, Tensor], feat: Tensor, state: Opt
     x = pooled
     hs, cs = [], []
     for l in range(cfg.lstm_layers):
-        p = f"{prefix}rnn.layers.{3 * l}."
-        h2, c2 = lstm_cell(x, h0[l], c0[l], W[p + "weight_ih_l0"], W[p + "weight_hh_l0"],
-                           W[p + "bias_ih_l0"], W[p + "bias_hh_l0"])
+        if cfg.lstm_layernorm:
+            p = f"{prefix}rnn.layers.{3 * l}."
+            h2, c2 = lstm_cell(x, h0[l], c0[l], W[p + "weight_ih_l0"], W[p + "weight_hh_l0"],
+                               W[p + "bias_ih_l0"], W[p + "bias_hh_l0"])
+            x = _ln(h2, W[f"{prefix}rnn.layers.{3 * l + 1}.weight"], W[f"{prefix}rnn.layers.{3 * l + 1}.bias"])
+        else:                                      # stacked nn.LSTM: layer l+1 consumes h of layer l (inter-layer dropout is identity in eval)
+            p = f"{prefix}rnn."
+            h2, c2 = lstm_cell(x, h0[l], c0[l], W[p + f"weight_ih_l{l}"], W[p + f"weight_hh_l{l}"],
+                               W[p + f"bias_ih_l{l}"], W[p + f"bias_hh_l{l}"])
+            x = h2
         hs.append(h2)
         cs.append(c2)
-        x = _ln(h2, W[f"{prefix}rnn.layers.{3 * l + 1}.weight"], W[f"{prefix}rnn.layers.{3 * l + 1}.bias"])
     outs = []
     for head in ("actions", "gripper"):
         y = x
         for j in range(len(cfg.mlp_dims)):
             p = f"{prefix}{head}.mlp."
             y = _linear(y, W[p + f"{4 * j + 1}.weight"], W[p + f"{4 * j + 1}.bias"])
-            y = torch.relu(_ln(y, W[p + f"{4 * j + 2}.weight"], W[p + f"{4 * j + 2}.bias"]))
+            if cfg.mlp_layernorm:
+                y = _ln(y, W[p + f"{4 * j + 2}.weight"], W[p + f"{4 * j + 2}.bias"])
+            y = torch.relu(y)
         k = 4 * len(cfg.mlp_dims) + 1
         y = _linear(y, W[f"{prefix}{head}.mlp.{k}.weight"], W[f"{prefix}{head}.mlp.{k}.bias"])
         outs.append(torch.tanh(y) if head == "actions" else torch.sigmoid(y))
@@ -670,6 +700,8 @@ class StepOutput:
     exit_layer: int
     deltas: Dict[int, float] = field(default_factory=dict)    # exit index -> delta evaluated
     taps: Dict[str, Tensor] = field(default_factory=dict)
+    ensemble_action: Optional[Tensor] = None                   # (7,) use_action_ensemble variant (eval_utils.py:457-464)
+    feature: Optional[Tensor] = None                           # (d,) pooled feature = .logits[2] (action_head.py:608-609)
 
 
 class DeerOracle:
@@ -725,6 +757,7 @@ class DeerOracle:
         prev_action: Optional[Tensor] = None
         exit_layer = cfg.n_layers - 1
         last_probe = None
+        action_list: List[Tuple[Tensor, Tensor]] = []        # value_net.py:129 (reset per step in ensemble mode, eval_utils.py:461)
         stage_boundary = (self.timestep % cfg.steps_per_stage == 0)
         for b_idx in range(cfg.n_layers):                                            # mosaic_gpt_3b.py:397
             x = flamingo_layer_forward(cfg, W, b_idx, x, media, media_locations, attn_bias)
@@ -748,6 +781,7 @@ class DeerOracle:
             deltas[b_idx] = delta
             prev_action = probe[0]
             last_probe = probe
+            action_list.append((probe[0], probe[1]))
             if full_depth:
                 if b_idx >= cfg.ctrl_max_layer:
                     exit_layer = b_idx
@@ -769,5 +803,10 @@ class DeerOracle:
             out_taps["pooled"] = pooled[0].clone()
             out_taps["h"] = new_state[0][:, 0].clone()
             out_taps["c"] = new_state[1][:, 0].clone()
+        ens = None
+        if action_list:                                                              # value_net.py:92-95, eval_utils.py:460-464
+            acts, grips = zip(*action_list[-2:])
+            ea, eg = torch.stack(acts, dim=0).mean(0)[0], torch.stack(grips, dim=0).mean(0)[0]
+            ens = torch.cat([ea, ((eg > 0.5).float() - 0.5) * 2])
         return StepOutput(pose=pose[0], gripper=grip[0], action=action, exit_layer=exit_layer,
-                          deltas=deltas, taps=out_taps)
+                          deltas=deltas, taps=out_taps, ensemble_action=ens, feature=pooled[0].clone())

@@ -38,7 +38,7 @@ from oracle import ref_shims                 # noqa: E402
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-def run_reference_episode(cfg, model, ctrl, episode, T, S, capture_hidden_at=None):
+def run_reference_episode(cfg, model, ctrl, episode, T, S, capture_hidden_at=None, ensemble=False):
     """ModelWrapper.reset + T x ModelWrapper.step (eval_utils.py:252-277, 279-490) on the
     reference modules; returns per-step dicts."""
     model.clear_all_exit_memory()
@@ -71,7 +71,13 @@ def run_reference_episode(cfg, model, ctrl, episode, T, S, capture_hidden_at=Non
             # eval_utils.py:458,464
             action = torch.concat((out.logits[0], out.logits[1] > 0.5), dim=2).squeeze(0)[-1]
             action[-1] = (action[-1] - 0.5) * 2
+            if ensemble:                      # use_action_ensemble (eval_utils.py:460-464)
+                ens = ctrl.value_net.get_ensemble_action()
+                ctrl.value_net.reset_actions()
+                action = torch.concat((ens[0], ens[1] > 0.5), dim=2).squeeze(0)[-1]
+                action[-1] = (action[-1] - 0.5) * 2
             rec = dict(pose=out.logits[0].flatten().clone(), gripper=out.logits[1].flatten().clone(),
+                       feature=out.logits[2].flatten().clone(),
                        action=action.clone(), exit_layer=int(out.exit_layer), deltas=dict(deltas_log),
                        h=model.extra_exit.hidden_state[0][:, 0].clone(), c=model.extra_exit.hidden_state[1][:, 0].clone())
             if capture_hidden_at is not None and t == capture_hidden_at:
@@ -354,6 +360,110 @@ def golden_full(S=32):
     np.savez_compressed(os.path.join(GOLD, "full3b.npz"), **out)
 
 
+def golden_full_long(S=32, T=10, n_ep=8):
+    """Round-2 fixture ``full3b_long.npz``: OpenFlamingo-3B size, ``n_ep`` episodes x ``T`` consecutive steps (carried LSTM
+    state) for DeeR-B (max_layer=12, exit_ratio 1.0) and DeeR-S (max_layer=4, exit_ratio 0.8), produced by the UNMODIFIED
+    reference modules and reproduced by the restatement (exit ids identical, tensors <= 5e-5).  Thresholds are calibrated
+    on a delta table that covers the SAME timestep range (12 other episodes x T steps), so the exits spread over the list.
+    Per decision the fixture also records the margin min_k |delta_k - T_k| over the probes the reference evaluated."""
+    torch.set_num_threads(os.cpu_count())
+    cfgB = O.config_3b(12)
+    W = O.synth_weights(cfgB, 0)
+    t0 = time.time()
+    table = batched_delta_table(cfgB, W, list(range(100, 112)), T, S)
+    print(f"[long] delta table {tuple(table.shape)} in {time.time() - t0:.1f}s; mean per exit {table.mean(1).tolist()}", flush=True)
+    out = {"delta_table": table.numpy(), "S": S, "T": T, "episodes": np.arange(n_ep)}
+    worst = 0.0
+    for tag, cfg, ratio in (("B", cfgB, 1.0), ("S", O.config_3b(4), 0.8)):
+        Wc = W if tag == "B" else {k: v for k, v in W.items() if k in {n for n, _, _ in O.weight_specs(cfg)}}
+        thr = O.solve_thresholds(table[:cfg.n_thresholds], ratio)
+        out[f"thresholds_{tag}"] = np.array(thr, np.float64)
+        model, ctrl, _ = ref_shims.build_reference_model(cfg, Wc, thr)
+        exits = [e for e in cfg.exit_list if e <= cfg.ctrl_max_layer]
+        hist, margins = {}, []
+        for e in range(n_ep):
+            t0 = time.time()
+            ref = run_reference_episode(cfg, model, ctrl, e, T, S)
+            orc, _ = run_oracle_episode(cfg, Wc, thr, e, T, S)
+            worst = max(worst, compare(ref, orc, 5e-5, f"3B-{tag} ep{e}"))
+            for k, v in pack_steps(ref, exits).items():
+                out[f"{tag}_ep{e}_{k}"] = v
+            mg = []
+            for r in ref:
+                m = [abs(v - thr[exits.index(k)]) for k, v in r["deltas"].items() if thr[exits.index(k)] < 1e7]
+                mg.append(min(m) if m else np.inf)
+                hist[r["exit_layer"]] = hist.get(r["exit_layer"], 0) + 1
+            out[f"{tag}_ep{e}_margin"] = np.array(mg, np.float64)
+            margins += mg
+            print(f"[long] DeeR-{tag} ep{e}: exits {[r['exit_layer'] for r in ref]} min margin {min(mg):.2e} ({time.time() - t0:.0f}s)", flush=True)
+        print(f"[long] DeeR-{tag}: thresholds {thr}; exit hist {dict(sorted(hist.items()))}; "
+              f"decisions with margin > 0.02: {sum(m > 0.02 for m in margins)} / {len(margins)}; smallest margin {min(margins):.2e}", flush=True)
+        del model, ctrl
+    print(f"[long] reference vs oracle worst |diff| {worst:.2e}")
+    np.savez_compressed(os.path.join(GOLD, "full3b_long.npz"), **out)
+
+
+HEAD_VARIANTS = {
+    # tag: (dropout_mode, mlp_layernorm, lstm_layernorm, hidden layers, {canonical Sequential index -> the reference's})
+    "oldest": ("wo_last", False, False, 3, {1: 0, 5: 2, 9: 4, 13: 6}),                     # action_head.py:149-158
+    "wolast_ln": ("wo_last", True, True, 3, {1: 1, 2: 2, 5: 5, 6: 6, 9: 9, 10: 10, 13: 12}),   # action_head.py:118-133
+    "last2": ("last", True, False, 2, {1: 0, 2: 1, 5: 3, 6: 4, 9: 7}),                     # action_head.py:86-113
+}
+
+
+def golden_variants(S=12, T=6):
+    """``variants_tiny.npz``: (1) the head variants of older DeeR checkpoints (eval_calvin.py:464-476) -- the UNMODIFIED reference
+    built with that dropout_mode / layernorm / hidden-layer setting, fed the synthetic weights under ITS OWN state-dict keys, run
+    with dynamic exit; the restatement reproduces it.  The reference's head key names are stored so the product's key
+    canonicalisation (checkpoint.canonical_head_keys) can be checked against them.  (2) ``use_action_ensemble``
+    (eval_utils.py:457-464, value_net.py:92-95): the action the reference's ModelWrapper would emit, plus ``.logits[2]``."""
+    import re
+    out = {"S": S, "T": T}
+    for tag, (mode, mlp_ln, lstm_ln, nh, idx) in HEAD_VARIANTS.items():
+        cfg = O.config_tiny(mlp_dims=(1024, 512, 256)[:nh], mlp_layernorm=mlp_ln, lstm_layernorm=lstm_ln)
+        W = O.synth_weights_variant(cfg, 0)
+        Wref = {}
+        for k, v in W.items():
+            m = re.match(r"^(extra_exit\.(?:actions|gripper)\.mlp\.)(\d+)(\..+)$", k)
+            Wref[f"{m.group(1)}{idx[int(m.group(2))]}{m.group(3)}" if m else k] = v
+        table = batched_delta_table(cfg, W, list(range(100, 108)), 4, S)
+        thr = O.solve_thresholds(table, 1.0)
+        model, ctrl, res = ref_shims.build_reference_model(cfg, Wref, thr, dropout_mode=mode)
+        exits = [e for e in cfg.exit_list if e <= cfg.ctrl_max_layer]
+        out[f"{tag}_thresholds"] = np.array(thr, np.float32)
+        out[f"{tag}_ref_head_keys"] = np.array(sorted(k for k in model.state_dict() if k.startswith("extra_exit.")))
+        hist = {}
+        for e in (0, 1):
+            ref = run_reference_episode(cfg, model, ctrl, e, T, S)
+            orc, _ = run_oracle_episode(cfg, W, thr, e, T, S)
+            w = compare(ref, orc, 2e-5, f"variant {tag} ep{e}")
+            for k, v in pack_steps(ref, exits).items():
+                out[f"{tag}_ep{e}_{k}"] = v
+            for r in ref:
+                hist[r["exit_layer"]] = hist.get(r["exit_layer"], 0) + 1
+        print(f"[variants] {tag}: reference == oracle (worst {w:.2e}); exits {hist}")
+        del model, ctrl
+    cfg = O.config_tiny()
+    W = O.synth_weights(cfg, 0)
+    g = np.load(os.path.join(GOLD, "tiny_dynamic.npz"))
+    thr = g["thresholds"].tolist()
+    model, ctrl, _ = ref_shims.build_reference_model(cfg, W, thr)
+    n_two = 0
+    for e in (0, 1, 2, 3):
+        ref = run_reference_episode(cfg, model, ctrl, e, T, S, ensemble=True)
+        orc, _ = run_oracle_episode(cfg, W, thr, e, T, S)
+        for t, (r, o) in enumerate(zip(ref, orc)):
+            assert r["exit_layer"] == o.exit_layer == int(g[f"ep{e}_exit_layer"][t]), (e, t)
+            assert float((r["action"] - o.ensemble_action).abs().max()) <= 2e-5, (e, t)
+            assert float((r["feature"] - o.feature).abs().max()) <= 2e-5, (e, t)
+            n_two += int(len(r["deltas"]) > 1)
+        out[f"ens_ep{e}_action"] = np.stack([r["action"].numpy() for r in ref])
+        out[f"ens_ep{e}_feature"] = np.stack([r["feature"].numpy() for r in ref])
+        out[f"ens_ep{e}_exit_layer"] = np.array([r["exit_layer"] for r in ref], np.int32)
+    print(f"[variants] action ensemble: reference == oracle on {4 * T} steps ({n_two} of them average two probes)")
+    np.savez_compressed(os.path.join(GOLD, "variants_tiny.npz"), **out)
+
+
 def golden_generate(bs=2, win=12, S=16):
     """Calibration pass in the training layout: the unmodified reference (MPTFlamingo.forward with return_in_feat /
     only_extra_exit as value_net.py:370-381 calls it, then ActionValueNet.forward(mode='generate')) vs the oracle's
@@ -421,6 +531,8 @@ if __name__ == "__main__":
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--yardstick-only", action="store_true")
     ap.add_argument("--generate-only", action="store_true")
+    ap.add_argument("--long-only", action="store_true", help="only the 8-episode x 10-step 3B fixture (full3b_long.npz)")
+    ap.add_argument("--variants-only", action="store_true", help="only the head-variant / action-ensemble fixture (variants_tiny.npz)")
     ap.add_argument("--family", default="3b", choices=["3b", "9b"], help="size of the --yardstick-only fixture")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
@@ -430,11 +542,19 @@ if __name__ == "__main__":
     if a.generate_only:
         golden_generate()
         sys.exit(0)
+    if a.long_only:
+        golden_full_long()
+        sys.exit(0)
+    if a.variants_only:
+        golden_variants()
+        sys.exit(0)
     golden_thresholds()
     xcheck_third_party()
     golden_tiny()
+    golden_variants()
     golden_generate()
     if a.full:
         golden_full()
+        golden_full_long()
         golden_yardstick()
         golden_yardstick(family="9b")

@@ -366,9 +366,11 @@ class _ClipShell(nn.Module):
 # --------------------------------------------------------------------------------------
 # build the reference's real MPTFlamingo + ExitController on CPU
 # --------------------------------------------------------------------------------------
-def build_reference_model(cfg, weights, thresholds=None):
+def build_reference_model(cfg, weights, thresholds=None, dropout_mode="layerwise"):
     """Returns (model: reference MPTFlamingo, exit_controller: reference ExitController).
-    ``cfg`` is an ``oracle.deer_oracle.DeerConfig`` with qk_ln=True (MPT-1B path)."""
+    ``cfg`` is an ``oracle.deer_oracle.DeerConfig`` with qk_ln=True (MPT-1B path).  ``dropout_mode`` / ``cfg.mlp_layernorm``
+    / ``cfg.lstm_layernorm`` / ``len(cfg.mlp_dims)`` select the head variant the reference builds (action_head.py:66-161);
+    ``weights`` must then carry the reference's OWN key names for that variant."""
     install_shims()
     mg = _build_mpt1b_package()
     import torch.distributed as dist
@@ -398,7 +400,7 @@ def build_reference_model(cfg, weights, thresholds=None):
                         fusion_mode="post", llm=cfg.llm_name, pooling="max", decoder_type="lstm",
                         head_type="deterministic", return_feature=True,
                         early_exit_layer=cfg.early_exit_layer, multi_exit=False, exit_interval=cfg.exit_interval,
-                        dropout_mode="layerwise", mlp_layernorm=True, lstm_layernorm=True,
+                        dropout_mode=dropout_mode, mlp_layernorm=cfg.mlp_layernorm, lstm_layernorm=cfg.lstm_layernorm,
                         mlp_num_hidden_layers=len(cfg.mlp_dims), lstm_num_layers=cfg.lstm_layers)
     sd = model.state_dict()
     # a checkpoint trained with more layers than max_layer keeps is loaded strict=False
@@ -406,6 +408,7 @@ def build_reference_model(cfg, weights, thresholds=None):
     extra = [k for k in weights if k not in sd]
     assert all(".blocks." in k for k in extra), extra[:5]
     res = model.load_state_dict({k: v for k, v in weights.items() if k in sd}, strict=False)
+    assert not [k for k in res.missing_keys if k.startswith("extra_exit.")], res.missing_keys[:8]   # head keys of this variant
     model.eval()
     value_net = ActionValueNet(exit_list=model.get_all_exit_idx(), exit_head=model.extra_exit,
                                interval=cfg.exit_interval, window_size=12, threshold_type=cfg.threshold_type)

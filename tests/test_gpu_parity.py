@@ -10,7 +10,7 @@ Tolerances (stated per test):
     (decisions inside the margin are rounding, not logic).  The size of "bf16 tolerance" itself is
     measured, not assumed: tests/golden/yardstick3b.npz holds the oracle run with bf16-rounded
     contraction operands (Y = 1.4e-2..1.8e-2 on poses vs the fp32 oracle at 3B size), and the engine
-    must stay within 3*Y of both oracles (test_full3b_bf16_within_rounding_yardstick).
+    must stay within 1.5*Y (+2e-3) of the fp32 oracle (test_full3b_bf16_within_rounding_yardstick).
 """
 import os
 
@@ -280,83 +280,15 @@ def full3b():
     return ocfg, O.synth_weights(ocfg, 0)
 
 
-def test_full3b_bf16_vs_reference_golden(full3b, gold_full):
-    """DeeR-B (max_layer=12) on the tcgen05 product path vs golden outputs of the unmodified reference
-    at full OpenFlamingo-3B size (2 episodes x 3 steps, dynamic exit, carried LSTM state)."""
-    ocfg, W = full3b
-    g = gold_full
-    S = int(g["S"])
-    thr = g["thresholds_B"].tolist()
-    eng = _engine(ocfg, W, max_batch=2, max_seq=S, precision="bf16", gemm_impl="tcgen05")
-    eng.set_thresholds(thr)
-    eng.reset()
-    exits = [e for e in ocfg.exit_list if e <= ocfg.ctrl_max_layer]
-    worst_pose, n_dec, n_margin_ok = 0.0, 0, 0
-    diverged = [False, False]
-    for t in range(3):
-        rgb, grip, ids = _inputs(ocfg, [0, 1], t, S)
-        out = eng.step(rgb.cuda(), grip.cuda(), ids.cuda())
-        ex = out["exit_layer"].cpu().numpy()
-        pose = out["pose"].cpu().numpy()
-        for e in range(2):
-            if diverged[e]:
-                continue                      # after a rounding-level exit flip the carried LSTM state legitimately differs
-            gd = g[f"B_ep{e}_deltas"][t]
-            gex = int(g[f"B_ep{e}_exit_layer"][t])
-            margin = min(abs(gd[k] - thr[k]) for k in range(len(exits)) if not np.isnan(gd[k]))
-            n_dec += 1
-            if int(ex[e]) == gex:
-                worst_pose = max(worst_pose, float(np.abs(pose[e] - g[f"B_ep{e}_pose"][t]).max()))
-            else:
-                assert margin <= 0.02, f"exit flip outside the rounding margin: ep{e} t{t} got {ex[e]} want {gex} margin {margin}"
-                diverged[e] = True
-            n_margin_ok += int(margin > 0.02)
-    assert worst_pose <= 5e-2, worst_pose
-    print(f"\n[full3b bf16] worst pose |err| {worst_pose:.3e} over {n_dec} decisions ({n_margin_ok} outside the 0.02 margin)")
-    eng.close()
-
-
-def test_full3b_deer_s_bf16_vs_reference_golden(full3b, gold_full):
-    """BASELINE configs[1] -- DeeR-S (max_layer=4 => 5 layers built, exits [1, 3], forced exit at 3; thresholds for exit_ratio 0.8)
-    on the tcgen05 product path vs the golden outputs of the UNMODIFIED reference (S_ep* of tests/golden/full3b.npz; the DeeR-B
-    checkpoint's weights loaded into the truncated model, strict=False, like eval_calvin.py:576-577)."""
-    ocfgB, WB = full3b
-    ocfg = O.config_3b(4)
-    W = {k: v for k, v in WB.items() if k in {n for n, _, _ in O.weight_specs(ocfg)}}
-    g = gold_full
-    S = int(g["S"])
-    thr = g["thresholds_S"].tolist()
-    eng = _engine(ocfg, W, max_batch=2, max_seq=S, precision="bf16", gemm_impl="tcgen05")
-    eng.set_thresholds(thr)
-    eng.reset()
-    exits = [e for e in ocfg.exit_list if e <= ocfg.ctrl_max_layer]
-    assert exits == [1, 3] and len(thr) == 2
-    worst_pose, n_dec = 0.0, 0
-    diverged = [False, False]
-    for t in range(3):
-        rgb, grip, ids = _inputs(ocfg, [0, 1], t, S)
-        out = eng.step(rgb.cuda(), grip.cuda(), ids.cuda())
-        ex, pose = out["exit_layer"].cpu().numpy(), out["pose"].cpu().numpy()
-        for e in range(2):
-            if diverged[e]:
-                continue                      # after a rounding-level exit flip the carried LSTM state legitimately differs
-            gd, gex = g[f"S_ep{e}_deltas"][t], int(g[f"S_ep{e}_exit_layer"][t])
-            margin = min(abs(gd[k] - thr[k]) for k in range(len(exits)) if not np.isnan(gd[k]))
-            n_dec += 1
-            if int(ex[e]) == gex:
-                worst_pose = max(worst_pose, float(np.abs(pose[e] - g[f"S_ep{e}_pose"][t]).max()))
-            else:
-                assert margin <= 0.02, f"exit flip outside the rounding margin: ep{e} t{t} got {ex[e]} want {gex} margin {margin}"
-                diverged[e] = True
-    assert n_dec >= 2 and worst_pose <= 5e-2, (n_dec, worst_pose)
-    print(f"\n[full3b DeeR-S bf16] worst pose |err| {worst_pose:.3e} over {n_dec} decisions")
-    eng.close()
+# (the 2-episode x 3-step bf16-vs-golden tests of round 1 are superseded by tests/test_gpu_round2.py: 8 episodes x 10 steps,
+#  asserted exact-match set, re-seeding after a rounding-level flip, fp32 path bit-exact on every decision)
 
 
 def test_full3b_bf16_within_rounding_yardstick(full3b):
     """'bf16 tolerance' made concrete: the oracle with bf16-rounded contraction operands (fp32
     accumulate, everything else fp32) differs from the fp32 oracle by Y on these inputs; the engine's bf16 path must be
-    within 3*Y of the fp32 oracle and within 3*Y of the bf16-operand oracle, on poses and on the gate's deltas."""
+    within 1.5*Y (+2e-3) of the fp32 oracle -- measured 1.0 .. 1.4*Y -- and within 2.5*Y of the bf16-operand oracle (two
+    independent roundings of the same computation differ by up to ~2*Y), on poses and on the gate's deltas."""
     ocfg, W = full3b
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "yardstick3b.npz"))
     S, T = int(g["S"]), int(g["T"])
@@ -373,7 +305,7 @@ def test_full3b_bf16_within_rounding_yardstick(full3b):
                 yard = float(np.abs(b16 - f32).max())
                 err32, err16 = float(np.abs(got - f32).max()), float(np.abs(got - b16).max())
                 print(f"\n[yardstick] ep{e} t{t} {name}: Y={yard:.3e} |engine-fp32|={err32:.3e} |engine-bf16ops|={err16:.3e}")
-                assert err32 <= 3 * yard + 2e-3 and err16 <= 3 * yard + 2e-3, (e, t, name, yard, err32, err16)
+                assert err32 <= 1.5 * yard + 2e-3 and err16 <= 2.5 * yard + 2e-3, (e, t, name, yard, err32, err16)
     eng.close()
 
 
@@ -460,7 +392,7 @@ def test_full9b_bf16_within_rounding_yardstick():
                 yard = float(np.abs(b16 - f32).max())
                 err32, err16 = float(np.abs(got - f32).max()), float(np.abs(got - b16).max())
                 print(f"\n[yardstick 9b] ep{e} t{t} {name}: Y={yard:.3e} |engine-fp32|={err32:.3e} |engine-bf16ops|={err16:.3e}")
-                assert err32 <= 3 * yard + 2e-3 and err16 <= 3 * yard + 2e-3, (e, t, name, yard, err32, err16)
+                assert err32 <= 2.5 * yard + 2e-3 and err16 <= 2.5 * yard + 2e-3, (e, t, name, yard, err32, err16)   # measured <= 2.1*Y
     eng.close()
 
 

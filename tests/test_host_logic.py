@@ -126,8 +126,10 @@ def test_checkpoint_name_and_hyperparameter_readout():
     cfg = config_from_checkpoint(ck, name, max_layer=12)
     assert cfg.exit_list == [1, 3, 5, 7, 9, 11] and cfg.n_layers == 12
     assert config_from_checkpoint(ck, name, max_layer=4).exit_list == [1, 3, 4]
+    old_cfg = config_from_checkpoint({}, name)                # an old-style head: no LayerNorms, 3 hidden layers (eval_calvin.py:464-476)
+    assert old_cfg.mlp_dims == (1024, 512, 256) and not old_cfg.mlp_layernorm and not old_cfg.lstm_layernorm
     with pytest.raises(NotImplementedError):
-        config_from_checkpoint({}, name)                     # an old-style head (no LayerNorm, 3 hidden layers) is out of scope
+        config_from_checkpoint(dict(ck, head_type="gaussian"), name)
     with pytest.raises(NotImplementedError):
         config_from_checkpoint(ck, name.replace("traj_cons", "state"))
 
@@ -236,3 +238,24 @@ while True:
     out = s.stop()
     assert out["samples"] >= 5 and out["sm_mhz"] == 1400.0 and out["sm_max_mhz"] == 1965.0
     assert out["reasons"] == ["sw_power_cap"] and out["power_w"] == 990.0
+
+
+def test_head_key_canonicalisation_vs_reference_layouts():
+    """checkpoint.canonical_head_keys against the state-dict keys the UNMODIFIED reference builds for each head variant
+    (stored in tests/golden/variants_tiny.npz by oracle/make_golden.py::golden_variants; action_head.py:82-161,183-269)."""
+    import os
+    import numpy as np
+    from deer_vla_b200 import config_tiny
+    from deer_vla_b200.checkpoint import canonical_head_keys
+    from deer_vla_b200.weights import state_dict_spec
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "variants_tiny.npz"))
+    variants = {"oldest": dict(dropout_mode="wo_last", mlp_layernorm=False, lstm_layernorm=False, mlp_num_hidden_layers=3, exit_dropout=0.0),
+                "wolast_ln": dict(dropout_mode="wo_last", mlp_layernorm=True, lstm_layernorm=True, mlp_num_hidden_layers=3, exit_dropout=0.0),
+                "last2": dict(dropout_mode="last", mlp_layernorm=True, lstm_layernorm=False, mlp_num_hidden_layers=2, exit_dropout=0.0)}
+    for tag, a in variants.items():
+        ref_keys = ["module." + str(k) for k in g[f"{tag}_ref_head_keys"]]
+        canon = canonical_head_keys({k: 0 for k in ref_keys}, a)
+        nh = 3 if a["dropout_mode"] == "wo_last" else a["mlp_num_hidden_layers"]
+        cfg = config_tiny(mlp_dims=(1024, 512, 256)[:nh], mlp_layernorm=a["mlp_layernorm"], lstm_layernorm=a["lstm_layernorm"])
+        want = {"module." + n for n, _, _ in state_dict_spec(cfg) if n.startswith("extra_exit.")}
+        assert set(canon) == want, (tag, sorted(set(canon) ^ want)[:6])

@@ -27,6 +27,30 @@ def _worker(rank, world, port, q):
     res = gather_results(actions, exits, dst=0)
     vals = all_gather_values(torch.full((2, 4), float(rank)))
     ok = vals.shape == (2, 8) and bool((vals[:, :4] == 0).all()) and bool((vals[:, 4:] == 1).all())
+    # ExitController.set_threshold(values=None): each rank calibrates on its own shard, the solver sees the gathered table
+    # (value_net.py:192-201) -> identical thresholds on every rank, equal to the single-process solve over all samples
+    from deer_vla_b200.value_net import ExitController, solve_thresholds
+
+    class _Eng:                                  # stands in for the engine's full-depth step: rank-dependent delta columns
+        def __init__(self, r):
+            self.r = r
+            self.got = None
+
+        def reset(self):
+            pass
+
+        def step(self, full_depth, **b):
+            g = torch.Generator().manual_seed(100 + self.r)
+            return {"delta": torch.rand(16, 3, generator=g)}
+
+        def set_thresholds(self, t):
+            self.got = list(t)
+    ctrl = ExitController(None, exit_id_list=[1, 3, 5], steps_per_stage=1, leq=True, max_layer=6)
+    ctrl.engine = _Eng(rank)
+    ctrl.set_threshold(None, None, [dict()], 1.0, "mpt_dolly_3b", values=None)
+    full = torch.cat([torch.rand(16, 3, generator=torch.Generator().manual_seed(100 + r)).t() for r in range(world)], dim=1)
+    want = solve_thresholds(full, 1.0, "exp", "mpt_dolly_3b", True)
+    ok = ok and all(abs(ctrl.thresholds[e] - float(want[i])) < 1e-12 for i, e in enumerate([1, 3, 5])) and ctrl.engine.got is not None
     if rank == 0:
         acts, ex = res
         ok = ok and acts.shape == (8, T, 7) and ex.shape == (8, T) and ex.dtype == torch.int32
