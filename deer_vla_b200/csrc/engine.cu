@@ -5,6 +5,7 @@
 #include "attn_tc.cuh"
 #include "attn_tc5.cuh"
 #include "gemm.cuh"
+#include "head_fused.cuh"
 #include "kernels.cuh"
 
 #include <algorithm>
@@ -154,13 +155,31 @@ static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int
   } else {
     if ((lda & 7) || (ldw & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
       return set_err(g.err, DEER_E_INVALID, "tcgen05 GEMM needs 16-byte aligned operands (lda=%d ldw=%d)", lda, ldw);
+    // Tile configuration by a wave-count cost model (rounds up partial waves; per-SM tile cost / measured relative efficiency
+    // of each kernel, profiles/r01_gemm_microbench.txt): the 2-CTA 256x256 kernel wins whenever its 74 cluster slots fill, but
+    // a projection with few tiles (M = 896 rows of a 28-episode shard x N = 2048: 32 tiles on 74 pairs) runs 1.4x faster as
+    // 112 one-CTA 128x128 tiles.  m_dev-clamped launches are sized for the host bound M (the first probes of a step).
     const int mt = (M + 127) / 128;
+    auto waves = [](long tiles, int slots) { return (double)((tiles + slots - 1) / slots); };
+    const double c2 = (N >= 256) ? waves((long)((M + 255) / 256) * ((N + 255) / 256), DEER_NUM_SMS / 2) * 32768.0 / 1.00 : 1e30;
+    const double c256 = (N >= 256) ? waves((long)mt * ((N + 255) / 256), DEER_NUM_SMS) * 32768.0 / 0.83 : 1e30;
+    const double c128 = (N >= 128) ? waves((long)mt * ((N + 127) / 128), DEER_NUM_SMS) * 16384.0 / 0.75 : 1e30;
+    const double c64 = waves((long)mt * ((N + 63) / 64), DEER_NUM_SMS) * 8192.0 / 0.55;
+    static const bool old_pick = getenv("DEER_GEMM_OLD_PICK") != nullptr;
     int BN;
-    const bool use2 = (impl != 2) && N >= 256 && ((M + 255) / 256) * ((N + 255) / 256) >= 32;
-    if (use2) BN = 128;                       // B box = this CTA's 128-row half of the 256-wide tile
-    else if (mt * ((N + 255) / 256) >= 2 * DEER_NUM_SMS && N >= 256) BN = 256;
-    else if (mt * ((N + 127) / 128) >= DEER_NUM_SMS && N >= 128) BN = 128;
-    else BN = 64;
+    bool use2;
+    if (old_pick) {
+      use2 = (impl != 2) && N >= 256 && ((M + 255) / 256) * ((N + 255) / 256) >= 32;
+      if (use2) BN = 128;
+      else if (mt * ((N + 255) / 256) >= 2 * DEER_NUM_SMS && N >= 256) BN = 256;
+      else if (mt * ((N + 127) / 128) >= DEER_NUM_SMS && N >= 128) BN = 128;
+      else BN = 64;
+    } else {
+      const double best1 = std::min(c256, std::min(c128, c64));
+      use2 = (impl != 2) && c2 <= best1;
+      if (use2) BN = 128;                     // B box = this CTA's 128-row half of the 256-wide tile
+      else BN = (c256 <= c128 && c256 <= c64) ? 256 : (c128 <= c64 ? 128 : 64);
+    }
     TmapKey ka{A, (uint64_t)a_rows, (uint64_t)K, (uint64_t)lda, 128u};
     TmapKey kb{W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)BN};
     auto ia = g.tmaps.find(ka);
@@ -356,6 +375,8 @@ struct deer_ctx {
   uint8_t* u8_stage[2] = {nullptr, nullptr}; size_t u8_cap[2] = {0, 0};
   // generate (calibration) mode
   const int32_t* gen_commit_layer = nullptr; float *pend_h = nullptr, *pend_c = nullptr; uint8_t* pend_flag = nullptr;
+  // fused exit-head probe (head_fused.cuh): persistent cooperative kernel for active sets of <= hf_mr episodes
+  bool hf_ok = false; int hf_mr = 0, hf_lda = 0, hf_grid = 0; size_t hf_smem = 0; unsigned long long* hf_bar = nullptr;
   GemmCtx gemm;
   LaunchStats stats;
   int64_t steps = 0;
@@ -732,6 +753,33 @@ static int upload_f32(deer_ctx* c, const std::vector<float>& v, float** dst) {
   return DEER_OK;
 }
 
+// The fused probe kernel serves the trained head configuration on the bf16 product path; anything else keeps the per-op path.
+static int setup_head_fused(deer_ctx* c) {
+  const deer_config& f = c->cfg;
+  c->hf_ok = false;
+  if (getenv("DEER_HEAD_FUSED") && atoi(getenv("DEER_HEAD_FUSED")) == 0) return DEER_OK;
+  if (c->dtype != 0 || f.gemm_impl != DEER_GEMM_TCGEN05) return DEER_OK;
+  if (!f.lstm_layernorm || !f.mlp_layernorm || f.mlp_dim2 > 0) return DEER_OK;
+  const int D = f.d_model, H = f.lstm_hidden, d0 = f.mlp_dim0, d1 = f.mlp_dim1, LL = f.lstm_layers;
+  if (H % 128 || d0 % 128 || d1 % 128 || D % 64 || d1 > 512 || H > 2048 || d0 > 2048 || LL > HF_MAX_LAYERS) return DEER_OK;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, c->device));
+  const int G = std::min(DEER_NUM_SMS, prop.multiProcessorCount);
+  if (H / 8 > G || 2 * d0 / 16 > G || 2 * d1 / 8 > G || !prop.cooperativeLaunch) return DEER_OK;
+  const int kmax = std::max(std::max(D + H, 2 * H), 2 * d0);
+  const int lda = kmax + 32;                       // 64-byte skew: conflict-free 16-byte shared loads (head_fused.cuh)
+  int mr = 32;
+  if ((size_t)mr * lda * 2 > 200 * 1024) mr = 16;
+  if ((size_t)mr * lda * 2 > 200 * 1024) return DEER_OK;
+  const size_t smem = std::max((size_t)mr * lda * 2, (size_t)HF_WARPS * mr * 32 * 4);
+  if (cudaFuncSetAttribute(head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return DEER_OK; }
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, head_fused_kernel, HF_THREADS, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); return DEER_OK; }
+  RET(dalloc(c, reinterpret_cast<void**>(&c->hf_bar), 256, false, true));
+  c->hf_mr = mr; c->hf_lda = lda; c->hf_grid = G; c->hf_smem = smem; c->hf_ok = true;
+  return DEER_OK;
+}
+
 extern "C" int deer_finalize_weights(deer_ctx* c) {
   if (!c) return set_err(nullptr, DEER_E_INVALID, "null ctx");
   if (c->finalized) return DEER_OK;
@@ -869,6 +917,7 @@ extern "C" int deer_finalize_weights(deer_ctx* c) {
     RET(pack_f32(c, pa + io + ".weight", {6, dl}, &c->w3_pose)); RET(pack_f32(c, pa + io + ".bias", {6}, &c->b3_pose));
     RET(pack_f32(c, pg + io + ".weight", {1, dl}, &c->w3_grip)); RET(pack_f32(c, pg + io + ".bias", {1}, &c->b3_grip));
   }
+  RET(setup_head_fused(c));
   CK(cudaDeviceSynchronize());
   for (auto& kv : c->staged) if (kv.second.dev) cudaFree(kv.second.dev);
   c->staged.clear();
@@ -1086,6 +1135,34 @@ template <typename T> struct StepImpl {
     const int D = f.d_model, H = f.lstm_hidden, LL = f.lstm_layers, Bm = f.max_batch, d0 = f.mlp_dim0, d1 = f.mlp_dim1;
     const int* nd = nact();
     const EpisodeMeta& m = c->meta[cur];
+    if (c->hf_ok && n <= c->hf_mr) {
+      HeadFusedParams hp{};
+      hp.x = c->x[cur]; hp.valid_len = m.valid_len; hp.slot = m.slot; hp.h_state = c->h_state; hp.c_state = c->c_state;
+      hp.S = S; hp.D = D; hp.H = H; hp.LL = LL; hp.nstride = Bm; hp.d0 = d0; hp.d1 = d1; hp.mr = c->hf_mr; hp.lda = c->hf_lda;
+      for (int l = 0; l < LL; ++l) {
+        hp.w_cat[l] = reinterpret_cast<const bf16*>(c->lstm[l].w_cat); hp.b_sum[l] = c->lstm[l].b_sum;
+        hp.ln_g[l] = c->lstm[l].ln_g; hp.ln_b[l] = c->lstm[l].ln_b;
+      }
+      hp.w_mlp1 = reinterpret_cast<const bf16*>(c->w_mlp1); hp.b_mlp1 = c->b_mlp1; hp.g_mlp1 = c->g_mlp1; hp.be_mlp1 = c->be_mlp1;
+      hp.w_mlp2_pose = reinterpret_cast<const bf16*>(c->w_mlp2_pose); hp.w_mlp2_grip = reinterpret_cast<const bf16*>(c->w_mlp2_grip);
+      hp.b_mlp2 = c->b_mlp2; hp.g_mlp2 = c->g_mlp2; hp.be_mlp2 = c->be_mlp2;
+      hp.w3_pose = c->w3_pose; hp.b3_pose = c->b3_pose; hp.w3_grip = c->w3_grip; hp.b3_grip = c->b3_grip;
+      hp.pooled = c->pooled; hp.mlp1 = c->mlp1; hp.mlp2 = c->mlp2; hp.cand_h = c->cand_h; hp.cand_c = c->cand_c;
+      hp.cur_pose = c->cur_pose; hp.cur_grip = c->cur_grip; hp.bar = c->hf_bar; hp.n_host = n; hp.n_dev = nd;
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3(c->hf_grid); lc.blockDim = dim3(HF_THREADS); lc.dynamicSmemBytes = c->hf_smem; lc.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+      lc.attrs = at; lc.numAttrs = 1;
+      const cudaError_t le = cudaLaunchKernelEx(&lc, head_fused_kernel, hp);
+      if (le != cudaSuccess) return set_err(&c->err, DEER_E_CUDA, "head_fused launch failed: %s", cudaGetErrorString(le));
+      c->stats.total++; c->stats.step++;
+      if (f.debug_taps) {
+        tap_scatter_kernel<float><<<dim3(n, 1), 256, 0, st>>>(c->pooled, c->tap_pooled, nullptr, (size_t)D, n, nd);
+        KLAUNCH_CHECK("tap_pooled");
+      }
+      return DEER_OK;
+    }
     launch_k(maxpool_kernel<T>, dim3((D + 255) / 256, n), dim3(256), 0, st, c->gemm.pdl, c->x[cur], m.valid_len, tp(c->a0), D + H, c->pooled, S, D, n, nd);
     KLAUNCH_CHECK("maxpool");
     if (f.debug_taps) {

@@ -316,3 +316,50 @@ def test_deer_pth_through_factory(tmp_path):
         o = O.DeerOracle(ocfg, W).step(rgb[0].cpu(), grip[0].cpu(), ids[0].cpu(), full_depth=True)
         assert np.abs(out["pose"][0].cpu().numpy() - o.pose.numpy()).max() <= 2e-4, variant
         eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# 5. the persistent fused exit-head probe (head_fused.cuh) against the per-op path and the oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 7, 20, 32])
+def test_fused_head_probe_vs_per_op_path_and_oracle(n):
+    """Active sets of <= 32 episodes run every probe in ONE cooperative kernel (max-pool, LayerNormLSTM x4, both MLP heads).
+    Same inputs through the per-op path (DEER_HEAD_FUSED=0: tcgen05 GEMM + cell + LN launches): poses / deltas / carried state
+    agree to bf16 rounding noise; and both sit at bf16 tolerance from the fp32 oracle.  n = 20, 32 use both 16-row MMA tiles."""
+    ocfg = O.config_tiny()
+    W = O.synth_weights(ocfg, 0)
+    S, T = 12, 3
+    eps = list(range(n))
+    outs = {}
+    for fused in (1, 0):
+        os.environ["DEER_HEAD_FUSED"] = str(fused)
+        try:
+            eng = _engine(ocfg, W, max_batch=n, max_seq=S, precision="bf16", gemm_impl="tcgen05")
+        finally:
+            os.environ.pop("DEER_HEAD_FUSED", None)
+        eng.reset()
+        res = []
+        for t in range(T):
+            o = eng.step(*_inputs(ocfg, eps, t, S), full_depth=True)
+            res.append({k: v.cpu().numpy().copy() for k, v in o.items()})
+        res.append({"h": np.stack([eng.get_state(i)[0] for i in range(n)]), "c": np.stack([eng.get_state(i)[1] for i in range(n)])})
+        launches = eng.stats().kernel_launches_last_step
+        outs[fused] = (res, launches)
+        eng.close()
+    (a, la), (b, lb) = outs[1], outs[0]
+    assert la < lb - 40, (la, lb)                                   # 4 probes x (15 -> 1) launches fewer
+    for t in range(T):
+        assert np.array_equal(a[t]["exit_layer"], b[t]["exit_layer"])
+        assert np.abs(a[t]["pose"] - b[t]["pose"]).max() <= 6e-3, (t, np.abs(a[t]["pose"] - b[t]["pose"]).max())
+        assert np.abs(a[t]["delta"] - b[t]["delta"]).max() <= 6e-3
+        assert np.abs(a[t]["gripper"] - b[t]["gripper"]).max() <= 6e-3
+    assert np.abs(a[T]["h"] - b[T]["h"]).max() <= 1e-2 and np.abs(a[T]["c"] - b[T]["c"]).max() <= 2e-2
+    orc = O.DeerOracle(ocfg, W)
+    orc.reset()
+    e = n - 1                                                        # the last row (second MMA tile when n > 16)
+    for t in range(T):
+        o = orc.step(O.synth_image(ocfg, e, t, 0), O.synth_image(ocfg, e, t, 1), O.synth_tokens(ocfg, e, S), full_depth=True)
+        assert np.abs(a[t]["pose"][e] - o.pose.numpy()).max() <= 4e-2
+        d = a[t]["delta"][e]
+        for k, ex in enumerate([x for x in ocfg.exit_list if x <= ocfg.ctrl_max_layer]):
+            assert abs(d[k] - o.deltas[ex]) <= 8e-2
