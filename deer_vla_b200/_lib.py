@@ -79,6 +79,7 @@ SYMBOLS = {
     "deer_op_gemm": (C.c_int, [C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                                _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P]),
     "deer_attn_debug": (C.c_int, [C.c_int, _P, C.c_int]),
+    "deer_head_debug": (C.c_int, [C.c_int, _P, C.c_int]),
     "deer_op_pv_probe": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "deer_op_attention": (C.c_int, [C.c_int, C.c_int, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, C.c_float, _P]),

@@ -210,6 +210,7 @@ static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int
 
 static std::map<TmapKey, CUtensorMap> g_attn_tmaps;
 static long long* g_attn_dbg = nullptr;       // optional per-CTA phase-cycle counters (deer_attn_debug)
+static long long* g_head_dbg = nullptr;       // optional phase timestamps of the fused head probe (deer_head_debug)
 static const CUtensorMap* attn_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box) {
   TmapKey k{ptr, rows, cols, ld, box};
   auto it = g_attn_tmaps.find(k);
@@ -761,7 +762,7 @@ static int setup_head_fused(deer_ctx* c) {
   if (c->dtype != 0 || f.gemm_impl != DEER_GEMM_TCGEN05) return DEER_OK;
   if (!f.lstm_layernorm || !f.mlp_layernorm || f.mlp_dim2 > 0) return DEER_OK;
   const int D = f.d_model, H = f.lstm_hidden, d0 = f.mlp_dim0, d1 = f.mlp_dim1, LL = f.lstm_layers;
-  if (H % 128 || d0 % 128 || d1 % 128 || D % 64 || d1 > 512 || H > 2048 || d0 > 2048 || LL > HF_MAX_LAYERS) return DEER_OK;
+  if (H % 128 || d0 % 128 || d1 % 128 || D % 64 || d1 > 512 || H > 1024 || d0 > 1024 || LL > HF_MAX_LAYERS) return DEER_OK;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, c->device));
   const int G = std::min(DEER_NUM_SMS, prop.multiProcessorCount);
@@ -1148,7 +1149,7 @@ template <typename T> struct StepImpl {
       hp.b_mlp2 = c->b_mlp2; hp.g_mlp2 = c->g_mlp2; hp.be_mlp2 = c->be_mlp2;
       hp.w3_pose = c->w3_pose; hp.b3_pose = c->b3_pose; hp.w3_grip = c->w3_grip; hp.b3_grip = c->b3_grip;
       hp.pooled = c->pooled; hp.mlp1 = c->mlp1; hp.mlp2 = c->mlp2; hp.cand_h = c->cand_h; hp.cand_c = c->cand_c;
-      hp.cur_pose = c->cur_pose; hp.cur_grip = c->cur_grip; hp.bar = c->hf_bar; hp.n_host = n; hp.n_dev = nd;
+      hp.cur_pose = c->cur_pose; hp.cur_grip = c->cur_grip; hp.bar = c->hf_bar; hp.n_host = n; hp.n_dev = nd; hp.dbg = g_head_dbg;
       cudaLaunchConfig_t lc = {};
       lc.gridDim = dim3(c->hf_grid); lc.blockDim = dim3(HF_THREADS); lc.dynamicSmemBytes = c->hf_smem; lc.stream = st;
       cudaLaunchAttribute at[1];
@@ -1690,6 +1691,15 @@ extern "C" int deer_attn_debug(int enable, long long* host_out, int n) {
   if (enable && !g_attn_dbg) { cudaMalloc(reinterpret_cast<void**>(&g_attn_dbg), 512 * 8 * sizeof(long long)); cudaMemset(g_attn_dbg, 0, 512 * 8 * sizeof(long long)); }
   if (host_out && g_attn_dbg) { cudaDeviceSynchronize(); cudaMemcpy(host_out, g_attn_dbg, std::min(n, 512 * 8) * sizeof(long long), cudaMemcpyDeviceToHost); }
   if (!enable && g_attn_dbg) { cudaFree(g_attn_dbg); g_attn_dbg = nullptr; }
+  return DEER_OK;
+}
+
+// tuning aid: %globaltimer (ns) of CTA 0 at the phase boundaries of the LAST fused head probe: [0] entry, then per grid barrier
+// k = 1..layers+3 the pair ([2k-1] arrival, [2k] release), [2*(layers+3)+1] exit
+extern "C" int deer_head_debug(int enable, long long* host_out, int n) {
+  if (enable && !g_head_dbg) { cudaMalloc(reinterpret_cast<void**>(&g_head_dbg), 64 * sizeof(long long)); cudaMemset(g_head_dbg, 0, 64 * sizeof(long long)); }
+  if (host_out && g_head_dbg) { cudaDeviceSynchronize(); cudaMemcpy(host_out, g_head_dbg, std::min(n, 64) * sizeof(long long), cudaMemcpyDeviceToHost); }
+  if (!enable && g_head_dbg) { cudaFree(g_head_dbg); g_head_dbg = nullptr; }
   return DEER_OK;
 }
 

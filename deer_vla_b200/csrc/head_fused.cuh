@@ -48,6 +48,7 @@ struct HeadFusedParams {
   float *cur_pose, *cur_grip;
   unsigned long long* bar;   // grid barrier counter (monotonic; every launch adds gridDim.x * (LL + 3))
   int n_host; const int* n_dev;
+  long long* dbg;            // optional [16]: %globaltimer (ns) of CTA 0 at every phase boundary (tuning only)
 };
 
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
@@ -143,44 +144,53 @@ __device__ __forceinline__ float hf_reduce(const float* red, int mr, int ncols, 
   return s;
 }
 
-// one warp: LayerNorm (two-pass fp32, eps 1e-5) of a `len`-long fp32 row (len % 128 == 0, <= 2048) from global memory (written by
-// other CTAs: L2-coherent loads), optional ReLU, bf16 into shared memory
-__device__ __forceinline__ void hf_ln_row_to_smem(const float* src, int len, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                  bool relu, bf16* dst, int lane) {
-  float4 v[16];
+// one warp: LayerNorm (two-pass fp32, eps 1e-5) of up to FOUR `len`-long fp32 rows (len % 128 == 0, <= 1024) from global memory
+// (written by other CTAs: L2-coherent loads), optional ReLU, bf16 into shared memory.  All rows' loads are issued before the first
+// reduction, so the warp pays one L2 round trip for its four rows instead of four.
+__device__ __forceinline__ void hf_ln_rows_to_smem(const float* const (&src)[4], int len, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, bool relu, bf16* const (&dst)[4], int lane) {
+  float4 v[4][8];
   const int nv = len >> 7;
-  float s = 0.0f;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    if (i < nv) {
-      v[i] = __ldcg(reinterpret_cast<const float4*>(src + (lane + 32 * i) * 4));
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      v[q][i] = (src[q] != nullptr && i < nv) ? __ldcg(reinterpret_cast<const float4*>(src[q] + (lane + 32 * i) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float inv_len = 1.0f / static_cast<float>(len);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (src[q] == nullptr) continue;                       // warp-uniform
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += (v[q][i].x + v[q][i].y) + (v[q][i].z + v[q][i].w);
+    const float mean = warp_sum(s) * inv_len;
+    float sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < nv) {
+        const float a = v[q][i].x - mean, b = v[q][i].y - mean, c = v[q][i].z - mean, d = v[q][i].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_len + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < nv) {
+        const int j = (lane + 32 * i) * 4;
+        const float4 g = *reinterpret_cast<const float4*>(gamma + j);
+        const float4 b = *reinterpret_cast<const float4*>(beta + j);
+        float4 y;
+        y.x = (v[q][i].x - mean) * rstd * g.x + b.x; y.y = (v[q][i].y - mean) * rstd * g.y + b.y;
+        y.z = (v[q][i].z - mean) * rstd * g.z + b.z; y.w = (v[q][i].w - mean) * rstd * g.w + b.w;
+        if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+        uint2 o; o.x = pack_bf16x2(y.x, y.y); o.y = pack_bf16x2(y.z, y.w);
+        *reinterpret_cast<uint2*>(dst[q] + j) = o;
+      }
     }
   }
-  const float mean = warp_sum(s) / static_cast<float>(len);
-  float q = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    if (i < nv) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      q += (a * a + b * b) + (c * c + d * d);
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(len) + 1e-5f);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    if (i < nv) {
-      const int j = (lane + 32 * i) * 4;
-      const float4 g = *reinterpret_cast<const float4*>(gamma + j);
-      const float4 b = *reinterpret_cast<const float4*>(beta + j);
-      float4 y;
-      y.x = (v[i].x - mean) * rstd * g.x + b.x; y.y = (v[i].y - mean) * rstd * g.y + b.y;
-      y.z = (v[i].z - mean) * rstd * g.z + b.z; y.w = (v[i].w - mean) * rstd * g.w + b.w;
-      if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-      uint2 o; o.x = pack_bf16x2(y.x, y.y); o.y = pack_bf16x2(y.z, y.w);
-      *reinterpret_cast<uint2*>(dst + j) = o;
-    }
-  }
+}
+__device__ __forceinline__ void hf_zero_row(bf16* row, int len, int lane) {
+  for (int j = lane * 8; j < len; j += 256) *reinterpret_cast<uint4*>(row + j) = make_uint4(0u, 0u, 0u, 0u);
 }
 // fp32 row (global, possibly written by other CTAs) -> bf16 shared memory, len % 4 == 0
 __device__ __forceinline__ void hf_copy_row_to_smem(const float* src, int len, bf16* dst, int lane) {
@@ -212,6 +222,7 @@ head_fused_kernel(const HeadFusedParams p) {
   const int n1 = 2 * d0 / 16;                              // MLP1 items: 16 columns
   const int n2 = 2 * d1 / 8;                               // MLP2 items: 8 columns
 
+  if (p.dbg != nullptr && cta == 0 && threadIdx.x == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); p.dbg[0] = (long long)_t; }
   // ---- L2 prefetch of every weight row this CTA will stream, in phase order (82 MB over the grid; L2 holds 126 MB)
   for (int l = 0; l < LL; ++l) {
     const int K = (l == 0 ? D : H) + H;
@@ -253,8 +264,10 @@ head_fused_kernel(const HeadFusedParams p) {
   }
 #define HF_BARRIER()                                                          \
   do {                                                                        \
+    if (p.dbg != nullptr && cta == 0 && threadIdx.x == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); p.dbg[2 * n_bar + 1] = (long long)_t; } \
     ++n_bar;                                                                  \
     hf_grid_barrier(p.bar, bar_target + static_cast<unsigned long long>(n_bar) * G); \
+    if (p.dbg != nullptr && cta == 0 && threadIdx.x == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); p.dbg[2 * n_bar] = (long long)_t; } \
   } while (0)
   HF_BARRIER();
 
@@ -264,14 +277,24 @@ head_fused_kernel(const HeadFusedParams p) {
     const bool has_work = cta < nu;
     if (has_work) {
       // operand [rows, in | H]: layer input (pooled feature / LayerNorm of the previous layer's h) | carried h of this layer
-      for (int r = warp; r < rows_used; r += HF_WARPS) {
-        bf16* row = A_s + static_cast<size_t>(r) * lda;
+      // (a warp owns rows warp, warp + 8, warp + 16, warp + 24)
+      const float* src[4]; bf16* dst[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = warp + 8 * q;
+        dst[q] = A_s + static_cast<size_t>(r) * lda;
+        src[q] = (l > 0 && r < n) ? p.cand_h + (static_cast<size_t>(l - 1) * p.nstride + r) * H : nullptr;
+      }
+      if (l > 0) hf_ln_rows_to_smem(src, H, p.ln_g[l - 1], p.ln_b[l - 1], false, dst, lane);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = warp + 8 * q;
+        if (r >= rows_used) continue;
         if (r < n) {
-          if (l == 0) hf_copy_row_to_smem(p.pooled + static_cast<size_t>(r) * D, D, row, lane);
-          else hf_ln_row_to_smem(p.cand_h + (static_cast<size_t>(l - 1) * p.nstride + r) * H, H, p.ln_g[l - 1], p.ln_b[l - 1], false, row, lane);
-          hf_copy_row_to_smem(p.h_state + (static_cast<size_t>(p.slot[r]) * LL + l) * H, H, row + in, lane);
+          if (l == 0) hf_copy_row_to_smem(p.pooled + static_cast<size_t>(r) * D, D, dst[q], lane);
+          hf_copy_row_to_smem(p.h_state + (static_cast<size_t>(p.slot[r]) * LL + l) * H, H, dst[q] + in, lane);
         } else {
-          for (int j = lane * 8; j < K; j += 256) *reinterpret_cast<uint4*>(row + j) = make_uint4(0u, 0u, 0u, 0u);
+          hf_zero_row(dst[q], K, lane);
         }
       }
     }
@@ -314,11 +337,15 @@ head_fused_kernel(const HeadFusedParams p) {
   // ---- MLP layer 1 of both heads: [n, H] x [2*d0, H]^T, operand = LayerNorm of the last LSTM layer's h
   {
     if (cta < n1) {
-      for (int r = warp; r < rows_used; r += HF_WARPS) {
-        bf16* row = A_s + static_cast<size_t>(r) * lda;
-        if (r < n) hf_ln_row_to_smem(p.cand_h + (static_cast<size_t>(LL - 1) * p.nstride + r) * H, H, p.ln_g[LL - 1], p.ln_b[LL - 1], false, row, lane);
-        else for (int j = lane * 8; j < H; j += 256) *reinterpret_cast<uint4*>(row + j) = make_uint4(0u, 0u, 0u, 0u);
+      const float* src[4]; bf16* dst[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = warp + 8 * q;
+        dst[q] = A_s + static_cast<size_t>(r) * lda;
+        src[q] = (r < n) ? p.cand_h + (static_cast<size_t>(LL - 1) * p.nstride + r) * H : nullptr;
+        if (r >= n && r < rows_used) hf_zero_row(dst[q], H, lane);
       }
+      hf_ln_rows_to_smem(src, H, p.ln_g[LL - 1], p.ln_b[LL - 1], false, dst, lane);
     }
     __syncthreads();
     for (int it = cta; it < n1; it += G) {
@@ -348,11 +375,16 @@ head_fused_kernel(const HeadFusedParams p) {
   // ---- MLP layer 2: per head [n, d0] x [d1, d0]^T, operand = ReLU(LayerNorm(mlp1 half))
   {
     if (cta < n2) {
-      for (int rr = warp; rr < 2 * rows_used; rr += HF_WARPS) {
-        const int r = rr >> 1, head = rr & 1;
-        bf16* row = A_s + static_cast<size_t>(r) * lda + head * d0;
-        if (r < n) hf_ln_row_to_smem(p.mlp1 + static_cast<size_t>(r) * 2 * d0 + head * d0, d0, p.g_mlp1 + head * d0, p.be_mlp1 + head * d0, true, row, lane);
-        else for (int j = lane * 8; j < d0; j += 256) *reinterpret_cast<uint4*>(row + j) = make_uint4(0u, 0u, 0u, 0u);
+      for (int head = 0; head < 2; ++head) {               // a warp owns rows warp + 8q; one call per head
+        const float* src[4]; bf16* dst[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = warp + 8 * q;
+          dst[q] = A_s + static_cast<size_t>(r) * lda + head * d0;
+          src[q] = (r < n) ? p.mlp1 + static_cast<size_t>(r) * 2 * d0 + head * d0 : nullptr;
+          if (r >= n && r < rows_used) hf_zero_row(dst[q], d0, lane);
+        }
+        hf_ln_rows_to_smem(src, d0, p.g_mlp1 + head * d0, p.be_mlp1 + head * d0, true, dst, lane);
       }
     }
     __syncthreads();
@@ -417,6 +449,7 @@ head_fused_kernel(const HeadFusedParams p) {
       }
     }
   }
-  // pad the barrier count so that every launch adds exactly gridDim.x * (LL + 3) arrivals (n_bar == LL + 3 here)
+  if (p.dbg != nullptr && cta == 0 && threadIdx.x == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); p.dbg[2 * n_bar + 1] = (long long)_t; }
+  // every launch adds exactly gridDim.x * (LL + 3) barrier arrivals (n_bar == LL + 3 here)
 #undef HF_BARRIER
 }

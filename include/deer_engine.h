@@ -255,6 +255,9 @@ int deer_op_pv_probe(const void* P, const void* V, float* O, int K, int lbo_byte
 
 /* tuning aid: per-CTA cycle counters of the attention kernel's softmax warp (wait-S, pass 1, pass 2, wait-O, epilogue). */
 int deer_attn_debug(int enable, long long* host_out, int n);
+/* tuning aid: %globaltimer (ns) of CTA 0 at the phase boundaries of the last fused exit-head probe (head_fused.cuh): [0] entry,
+ * per grid barrier k = 1 .. lstm_layers + 3 the pair ([2k-1] arrival, [2k] release), then the exit. */
+int deer_head_debug(int enable, long long* host_out, int n);
 
 #ifdef __cplusplus
 }

@@ -526,6 +526,47 @@ def golden_yardstick(S=32, T=2, family="3b"):
     np.savez_compressed(os.path.join(GOLD, f"yardstick{family}.npz"), **out)
 
 
+def golden_yardstick_long(S=32):
+    """``yardstick3b_long.npz``: the rounding yardstick over the SAME rollouts as full3b_long.npz (8 episodes x 10 carried steps,
+    DeeR-B and DeeR-S, dynamic exit): the oracle with bf16-rounded contraction operands vs the reference goldens.  Where the
+    rounded oracle takes the reference's exit, |pose - golden pose| is one yardstick sample; where rounding flips the exit the
+    carried state is re-seeded from an fp32 oracle run beside it (== the goldens) -- exactly what the GPU test does with the
+    engine.  The test's pose bar is 1.5 x the largest sample."""
+    torch.set_num_threads(os.cpu_count())
+    g = np.load(os.path.join(GOLD, "full3b_long.npz"))
+    T, eps = int(g["T"]), g["episodes"].tolist()
+    W = O.synth_weights(O.config_3b(12), 0)
+    out = {}
+    for tag, ml in (("B", 12), ("S", 4)):
+        cfg = O.config_3b(ml)
+        Wc = {k: v for k, v in W.items() if k in {n for n, _, _ in O.weight_specs(cfg)}}
+        thr = g[f"thresholds_{tag}"].tolist()
+        errs, match = np.full((len(eps), T), np.nan, np.float32), np.zeros((len(eps), T), np.int8)
+        for i, e in enumerate(eps):
+            t0 = time.time()
+            f32, b16 = O.DeerOracle(cfg, Wc, thr), O.DeerOracle(cfg, Wc, thr)
+            f32.reset(); b16.reset()
+            ids = O.synth_tokens(cfg, e, S)
+            for t in range(T):
+                rgb, grip = O.synth_image(cfg, e, t, 0), O.synth_image(cfg, e, t, 1)
+                f32.set_timestep(t); b16.set_timestep(t)
+                a = f32.step(rgb, grip, ids)
+                with O.operand_rounding(torch.bfloat16):
+                    b = b16.step(rgb, grip, ids)
+                assert a.exit_layer == int(g[f"{tag}_ep{e}_exit_layer"][t])
+                if b.exit_layer == a.exit_layer:
+                    match[i, t] = 1
+                    errs[i, t] = float((b.pose - torch.from_numpy(g[f"{tag}_ep{e}_pose"][t])).abs().max())
+                else:
+                    b16.state = (f32.state[0].clone(), f32.state[1].clone())
+                    b16.cur_exit_id = f32.cur_exit_id
+            print(f"[yardstick-long] DeeR-{tag} ep{e}: matched {int(match[i].sum())}/{T}, max pose err {np.nanmax(errs[i]):.3e} ({time.time() - t0:.0f}s)", flush=True)
+        out[f"{tag}_pose_err"], out[f"{tag}_match"] = errs, match
+        print(f"[yardstick-long] DeeR-{tag}: Y_pose = {np.nanmax(errs):.3e} (mean {np.nanmean(errs):.3e}); rounded oracle keeps the reference's exit on "
+              f"{int(match.sum())}/{match.size} decisions", flush=True)
+    np.savez_compressed(os.path.join(GOLD, "yardstick3b_long.npz"), **out)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
@@ -534,8 +575,12 @@ if __name__ == "__main__":
     ap.add_argument("--long-only", action="store_true", help="only the 8-episode x 10-step 3B fixture (full3b_long.npz)")
     ap.add_argument("--variants-only", action="store_true", help="only the head-variant / action-ensemble fixture (variants_tiny.npz)")
     ap.add_argument("--family", default="3b", choices=["3b", "9b"], help="size of the --yardstick-only fixture")
+    ap.add_argument("--yardstick-long-only", action="store_true", help="only yardstick3b_long.npz (bf16-operand oracle over the full3b_long rollouts)")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
+    if a.yardstick_long_only:
+        golden_yardstick_long()
+        sys.exit(0)
     if a.yardstick_only:
         golden_yardstick(family=a.family)
         sys.exit(0)
@@ -556,5 +601,6 @@ if __name__ == "__main__":
     if a.full:
         golden_full()
         golden_full_long()
+        golden_yardstick_long()
         golden_yardstick()
         golden_yardstick(family="9b")

@@ -1,6 +1,7 @@
 #!/bin/bash
 # round 2, first GPU pass: parity tests + bench at 224 and 28 episodes per GPU + launch list at 28
 mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -1   # no-op when the shipped .so matches the sources
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > gpurun_out/r2a_gpu.txt 2>&1
 timeout 1500 python -m pytest tests -m gpu -q --tb=short -s > gpurun_out/r2a_tests_gpu.log 2>&1; echo "pytest -m gpu exit $?"; tail -3 gpurun_out/r2a_tests_gpu.log
 grep -h "^\[full3b\|^\[yardstick" gpurun_out/r2a_tests_gpu.log | head -40
