@@ -20,7 +20,8 @@ struct GemmEpi {
   const float* scale;  // device scalar (e.g. tanh(attn_gate)) or nullptr
   const float* resid;  // fp32 [M, ldr] or nullptr (may alias C)
   int ldr;
-  int dbg;             // 0 normal; tuning only: 2 = skip the epilogue's math and stores in the 2-CTA kernel (mainloop-only timing)
+  int dbg;             // 0 normal; tuning only: 2 = skip the epilogue's math and stores in the 2-CTA kernel (mainloop-only timing),
+                       // 4 = no L2 prefetch of the next tile's residual (A/B)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -652,6 +653,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t aph = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+      // The fp32 residual of the NEXT tile is pulled into L2 now -- one tile period (a whole main loop) ahead of its use, while
+      // this thread would otherwise wait for the accumulator: the epilogue's residual loads then cost an L2 hit instead of an
+      // HBM round trip (it was latency-bound on them: vit.out+res long_scoreboard 29 %, tensor pipe 54 %).
+      if (epi.resid != nullptr && epi.dbg != 4 && tile + num_clusters < num_tiles) {
+        const int nt = tile + num_clusters;
+        const int prow = (nt / n_blocks) * G::BM + static_cast<int>(rank) * 128 + lane_grp * 32 + lane;
+        const int pcol = (nt % n_blocks) * G::BN;
+        if (prow < M) {
+          for (int c = c_begin; c < c_end; ++c)
+            if (pcol + c * 32 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(epi.resid + static_cast<size_t>(prow) * epi.ldr + pcol + c * 32));
+        }
+      }
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const int row0 = m_blk * G::BM + static_cast<int>(rank) * 128 + lane_grp * 32;
@@ -662,7 +675,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
         tmem_ld_wait();
         const int col0 = n_blk * G::BN + c * 32;
-        if (epi.dbg == 0 && row0 < M && col0 < N) epi_store_coalesced(epi, sc, row0, col0, M, N, v, stage, lane);
+        if (epi.dbg != 2 && row0 < M && col0 < N) epi_store_coalesced(epi, sc, row0, col0, M, N, v, stage, lane);
       }
       tc_fence_before();
       __syncwarp();

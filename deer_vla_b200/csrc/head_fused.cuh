@@ -144,22 +144,29 @@ __device__ __forceinline__ float hf_reduce(const float* red, int mr, int ncols, 
   return s;
 }
 
-// one warp: LayerNorm (two-pass fp32, eps 1e-5) of up to FOUR `len`-long fp32 rows (len % 128 == 0, <= 1024) from global memory
-// (written by other CTAs: L2-coherent loads), optional ReLU, bf16 into shared memory.  All rows' loads are issued before the first
-// reduction, so the warp pays one L2 round trip for its four rows instead of four.
-__device__ __forceinline__ void hf_ln_rows_to_smem(const float* const (&src)[4], int len, const float* __restrict__ gamma,
-                                                   const float* __restrict__ beta, bool relu, bf16* const (&dst)[4], int lane) {
-  float4 v[4][8];
+// Operand staging.  Every global load of a staging call is issued BEFORE the first shared-memory store: the compiler cannot
+// move a (generic-pointer) load above a store it may alias, so a load-convert-store loop pays one full L2 round trip per
+// iteration (measured: 15 us per LSTM layer); batched, a call pays one.
+//
+// one warp: LayerNorm (two-pass fp32, eps 1e-5) of TWO `len`-long fp32 rows (len % 128 == 0, <= 1024) from global memory (written
+// by other CTAs: L2-coherent loads), optional ReLU, bf16 into shared memory.  src[q] == nullptr skips a row (warp-uniform).
+__device__ __forceinline__ void hf_ln_rows_to_smem(const float* const (&src)[2], int len, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, bool relu, bf16* const (&dst)[2], int lane) {
+  float4 v[2][8], g[8], bt[8];
   const int nv = len >> 7;
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int i = 0; i < 8; ++i) {
+    const int j = (lane + 32 * i) * 4;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      v[q][i] = (src[q] != nullptr && i < nv) ? __ldcg(reinterpret_cast<const float4*>(src[q] + (lane + 32 * i) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < 2; ++q)
+      v[q][i] = (src[q] != nullptr && i < nv) ? __ldcg(reinterpret_cast<const float4*>(src[q] + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    g[i] = (i < nv) ? __ldg(reinterpret_cast<const float4*>(gamma + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    bt[i] = (i < nv) ? __ldg(reinterpret_cast<const float4*>(beta + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   const float inv_len = 1.0f / static_cast<float>(len);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    if (src[q] == nullptr) continue;                       // warp-uniform
+  for (int q = 0; q < 2; ++q) {
+    if (src[q] == nullptr) continue;
     float s = 0.0f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += (v[q][i].x + v[q][i].y) + (v[q][i].z + v[q][i].w);
@@ -176,29 +183,42 @@ __device__ __forceinline__ void hf_ln_rows_to_smem(const float* const (&src)[4],
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (i < nv) {
-        const int j = (lane + 32 * i) * 4;
-        const float4 g = *reinterpret_cast<const float4*>(gamma + j);
-        const float4 b = *reinterpret_cast<const float4*>(beta + j);
         float4 y;
-        y.x = (v[q][i].x - mean) * rstd * g.x + b.x; y.y = (v[q][i].y - mean) * rstd * g.y + b.y;
-        y.z = (v[q][i].z - mean) * rstd * g.z + b.z; y.w = (v[q][i].w - mean) * rstd * g.w + b.w;
+        y.x = (v[q][i].x - mean) * rstd * g[i].x + bt[i].x; y.y = (v[q][i].y - mean) * rstd * g[i].y + bt[i].y;
+        y.z = (v[q][i].z - mean) * rstd * g[i].z + bt[i].z; y.w = (v[q][i].w - mean) * rstd * g[i].w + bt[i].w;
         if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
         uint2 o; o.x = pack_bf16x2(y.x, y.y); o.y = pack_bf16x2(y.z, y.w);
-        *reinterpret_cast<uint2*>(dst[q] + j) = o;
+        *reinterpret_cast<uint2*>(dst[q] + (lane + 32 * i) * 4) = o;
       }
     }
   }
 }
+// one warp: FOUR fp32 rows (global, possibly written by other CTAs) -> bf16 shared memory, len % 4 == 0; 1024 elements of every row
+// are in flight per pass
+__device__ __forceinline__ void hf_copy_rows_to_smem(const float* const (&src)[4], int len, bf16* const (&dst)[4], int lane) {
+  for (int j0 = 0; j0 < len; j0 += 1024) {
+    float4 v[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = j0 + (lane + 32 * i) * 4;
+        v[q][i] = (src[q] != nullptr && j < len) ? __ldcg(reinterpret_cast<const float4*>(src[q] + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = j0 + (lane + 32 * i) * 4;
+        if (src[q] != nullptr && j < len) {
+          uint2 o; o.x = pack_bf16x2(v[q][i].x, v[q][i].y); o.y = pack_bf16x2(v[q][i].z, v[q][i].w);
+          *reinterpret_cast<uint2*>(dst[q] + j) = o;
+        }
+      }
+  }
+}
 __device__ __forceinline__ void hf_zero_row(bf16* row, int len, int lane) {
   for (int j = lane * 8; j < len; j += 256) *reinterpret_cast<uint4*>(row + j) = make_uint4(0u, 0u, 0u, 0u);
-}
-// fp32 row (global, possibly written by other CTAs) -> bf16 shared memory, len % 4 == 0
-__device__ __forceinline__ void hf_copy_row_to_smem(const float* src, int len, bf16* dst, int lane) {
-  for (int j = lane * 4; j < len; j += 128) {
-    const float4 v = __ldcg(reinterpret_cast<const float4*>(src + j));
-    uint2 o; o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
-    *reinterpret_cast<uint2*>(dst + j) = o;
-  }
 }
 
 __global__ void __launch_bounds__(HF_THREADS, 1)
@@ -255,9 +275,13 @@ head_fused_kernel(const HeadFusedParams p) {
       const int vl = p.valid_len[r];
       float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
       const float* xr = p.x + static_cast<size_t>(r) * p.S * D + j;
-      for (int s = 0; s < vl; ++s) {
-        const float4 v = *reinterpret_cast<const float4*>(xr + static_cast<size_t>(s) * D);
-        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      for (int s0 = 0; s0 < vl; s0 += 8) {                 // eight token rows in flight per thread
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          v[u] = (s0 + u < vl) ? *reinterpret_cast<const float4*>(xr + static_cast<size_t>(s0 + u) * D) : m;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { m.x = fmaxf(m.x, v[u].x); m.y = fmaxf(m.y, v[u].y); m.z = fmaxf(m.z, v[u].z); m.w = fmaxf(m.w, v[u].w); }
       }
       *reinterpret_cast<float4*>(p.pooled + static_cast<size_t>(r) * D + j) = m;
     }
@@ -278,24 +302,23 @@ head_fused_kernel(const HeadFusedParams p) {
     if (has_work) {
       // operand [rows, in | H]: layer input (pooled feature / LayerNorm of the previous layer's h) | carried h of this layer
       // (a warp owns rows warp, warp + 8, warp + 16, warp + 24)
-      const float* src[4]; bf16* dst[4];
+      const float* hsrc[4]; const float* xsrc[4]; bf16* dst[4]; bf16* dsth[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int r = warp + 8 * q;
         dst[q] = A_s + static_cast<size_t>(r) * lda;
-        src[q] = (l > 0 && r < n) ? p.cand_h + (static_cast<size_t>(l - 1) * p.nstride + r) * H : nullptr;
+        dsth[q] = dst[q] + in;
+        hsrc[q] = (r < n) ? p.h_state + (static_cast<size_t>(p.slot[r]) * LL + l) * H : nullptr;
+        xsrc[q] = (r < n) ? ((l == 0) ? p.pooled + static_cast<size_t>(r) * D : p.cand_h + (static_cast<size_t>(l - 1) * p.nstride + r) * H) : nullptr;
+        if (r >= n && r < rows_used) hf_zero_row(dst[q], K, lane);
       }
-      if (l > 0) hf_ln_rows_to_smem(src, H, p.ln_g[l - 1], p.ln_b[l - 1], false, dst, lane);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int r = warp + 8 * q;
-        if (r >= rows_used) continue;
-        if (r < n) {
-          if (l == 0) hf_copy_row_to_smem(p.pooled + static_cast<size_t>(r) * D, D, dst[q], lane);
-          hf_copy_row_to_smem(p.h_state + (static_cast<size_t>(p.slot[r]) * LL + l) * H, H, dst[q] + in, lane);
-        } else {
-          hf_zero_row(dst[q], K, lane);
-        }
+      hf_copy_rows_to_smem(hsrc, H, dsth, lane);
+      if (l == 0) hf_copy_rows_to_smem(xsrc, D, dst, lane);
+      else {
+        const float* s01[2] = {xsrc[0], xsrc[1]}; bf16* d01[2] = {dst[0], dst[1]};
+        const float* s23[2] = {xsrc[2], xsrc[3]}; bf16* d23[2] = {dst[2], dst[3]};
+        hf_ln_rows_to_smem(s01, H, p.ln_g[l - 1], p.ln_b[l - 1], false, d01, lane);
+        if (two_m) hf_ln_rows_to_smem(s23, H, p.ln_g[l - 1], p.ln_b[l - 1], false, d23, lane);
       }
     }
     __syncthreads();
@@ -345,7 +368,10 @@ head_fused_kernel(const HeadFusedParams p) {
         src[q] = (r < n) ? p.cand_h + (static_cast<size_t>(LL - 1) * p.nstride + r) * H : nullptr;
         if (r >= n && r < rows_used) hf_zero_row(dst[q], H, lane);
       }
-      hf_ln_rows_to_smem(src, H, p.ln_g[LL - 1], p.ln_b[LL - 1], false, dst, lane);
+      const float* s01[2] = {src[0], src[1]}; bf16* d01[2] = {dst[0], dst[1]};
+      const float* s23[2] = {src[2], src[3]}; bf16* d23[2] = {dst[2], dst[3]};
+      hf_ln_rows_to_smem(s01, H, p.ln_g[LL - 1], p.ln_b[LL - 1], false, d01, lane);
+      if (two_m) hf_ln_rows_to_smem(s23, H, p.ln_g[LL - 1], p.ln_b[LL - 1], false, d23, lane);
     }
     __syncthreads();
     for (int it = cta; it < n1; it += G) {
@@ -375,7 +401,7 @@ head_fused_kernel(const HeadFusedParams p) {
   // ---- MLP layer 2: per head [n, d0] x [d1, d0]^T, operand = ReLU(LayerNorm(mlp1 half))
   {
     if (cta < n2) {
-      for (int head = 0; head < 2; ++head) {               // a warp owns rows warp + 8q; one call per head
+      for (int head = 0; head < 2; ++head) {               // a warp owns rows warp + 8q; per head, two rows per call
         const float* src[4]; bf16* dst[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -384,7 +410,10 @@ head_fused_kernel(const HeadFusedParams p) {
           src[q] = (r < n) ? p.mlp1 + static_cast<size_t>(r) * 2 * d0 + head * d0 : nullptr;
           if (r >= n && r < rows_used) hf_zero_row(dst[q], d0, lane);
         }
-        hf_ln_rows_to_smem(src, d0, p.g_mlp1 + head * d0, p.be_mlp1 + head * d0, true, dst, lane);
+        const float* s01[2] = {src[0], src[1]}; bf16* d01[2] = {dst[0], dst[1]};
+        const float* s23[2] = {src[2], src[3]}; bf16* d23[2] = {dst[2], dst[3]};
+        hf_ln_rows_to_smem(s01, d0, p.g_mlp1 + head * d0, p.be_mlp1 + head * d0, true, d01, lane);
+        if (two_m) hf_ln_rows_to_smem(s23, d0, p.g_mlp1 + head * d0, p.be_mlp1 + head * d0, true, d23, lane);
       }
     }
     __syncthreads();
