@@ -109,7 +109,7 @@ def _bf16_long(w3b, g, tag, use_graph):
         e_.set_thresholds(thr)
         e_.reset()
     n_strict = n_soft = n_soft_ok = n_reseed = 0
-    worst_pose = 0.0
+    worst_pose, pose_errs = 0.0, []
     for t in range(T):
         ins = _inputs(ocfg, eps, t, S)
         ts = torch.full((len(eps),), t, dtype=torch.int32, device="cuda")
@@ -129,26 +129,36 @@ def _bf16_long(w3b, g, tag, use_graph):
                 n_soft += 1
                 n_soft_ok += int(same)
             if same:
-                worst_pose = max(worst_pose, float(np.abs(pose[i] - g[f"{tag}_ep{e}_pose"][t]).max()))
+                pose_errs.append(float(np.abs(pose[i] - g[f"{tag}_ep{e}_pose"][t]).max()))
+                worst_pose = max(worst_pose, pose_errs[-1])
             else:                                     # rounding-level flip: re-seed this episode's LSTM state, keep checking
                 h, c = ref.get_state(i)
                 eng.set_state(i, h, c)
                 n_reseed += 1
     print(f"\n[full3b bf16 DeeR-{tag} graph={int(use_graph)}] exact-match set {n_strict}/{n_strict} (margin > {MARGIN}); inside the rounding band "
-          f"{n_soft_ok}/{n_soft} match; {n_reseed} re-seeds; worst |pose - reference| {worst_pose:.3e}")
+          f"{n_soft_ok}/{n_soft} match; {n_reseed} re-seeds; |pose - reference| worst {worst_pose:.3e} mean {np.mean(pose_errs):.3e}")
     eng.close(); ref.close()
-    return n_strict, n_soft, n_soft_ok, worst_pose
+    return n_strict, n_soft, n_soft_ok, worst_pose, float(np.mean(pose_errs))
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_full3b_bf16_vs_reference_long_golden(w3b, gold_long, use_graph):
+    """Pose bar = the rounding yardstick of THESE rollouts (tests/golden/yardstick3b_long.npz: the oracle with bf16-rounded
+    contraction operands against the same reference goldens, 8 episodes x 10 carried steps; it differs from the reference by
+    Y_max = 3.0e-2 / 4.5e-2 and Y_mean = 1.4e-2 / 1.7e-2 on DeeR-B / DeeR-S and itself flips 6 / 2 of the 80 decisions):
+    the engine must stay within 1.5 x Y_max (+2e-3) at its worst decision and within 1.5 x Y_mean on average
+    (measured: 1.0 / 1.26 x Y_max)."""
+    y = np.load(os.path.join(GOLD, "yardstick3b_long.npz"))
     tot_strict = 0
     for tag, min_strict in (("B", 10), ("S", 40)):
-        n_strict, n_soft, n_soft_ok, worst_pose = _bf16_long(w3b, gold_long, tag, use_graph)
+        n_strict, n_soft, n_soft_ok, worst_pose, mean_pose = _bf16_long(w3b, gold_long, tag, use_graph)
+        y_max, y_mean = float(np.nanmax(y[f"{tag}_pose_err"])), float(np.nanmean(y[f"{tag}_pose_err"]))
+        y_flips = int(y[f"{tag}_match"].size - y[f"{tag}_match"].sum())
         assert n_strict >= min_strict, (tag, n_strict)
         assert n_strict + n_soft == 80
-        assert n_soft_ok >= 0.6 * n_soft, (tag, n_soft_ok, n_soft)          # measured: see profiles/r02_parity_3b.txt
-        assert worst_pose <= 4.5e-2, (tag, worst_pose)                      # ~1.5 * Y_pose (1.8e-2) over 10 carried steps + 2e-3 ... measured below
+        assert (n_soft - n_soft_ok) <= y_flips + 4, (tag, n_soft_ok, n_soft, y_flips)   # flips inside the rounding band: no more than the rounded oracle's + 4
+        assert worst_pose <= 1.5 * y_max + 2e-3, (tag, worst_pose, y_max)
+        assert mean_pose <= 1.5 * y_mean, (tag, mean_pose, y_mean)
         tot_strict += n_strict
     assert tot_strict >= 40
 
