@@ -377,7 +377,7 @@ struct deer_ctx {
   // generate (calibration) mode
   const int32_t* gen_commit_layer = nullptr; float *pend_h = nullptr, *pend_c = nullptr; uint8_t* pend_flag = nullptr;
   // fused exit-head probe (head_fused.cuh): persistent cooperative kernel for active sets of <= hf_mr episodes
-  bool hf_ok = false; int hf_mr = 0, hf_lda = 0, hf_grid = 0; size_t hf_smem = 0; unsigned long long* hf_bar = nullptr;
+  bool hf_ok = false; int hf_mr = 0, hf_lda = 0, hf_grid = 0, hf_cluster = 1; size_t hf_smem = 0; unsigned long long* hf_bar = nullptr;
   GemmCtx gemm;
   LaunchStats stats;
   int64_t steps = 0;
@@ -762,11 +762,10 @@ static int setup_head_fused(deer_ctx* c) {
   if (c->dtype != 0 || f.gemm_impl != DEER_GEMM_TCGEN05) return DEER_OK;
   if (!f.lstm_layernorm || !f.mlp_layernorm || f.mlp_dim2 > 0) return DEER_OK;
   const int D = f.d_model, H = f.lstm_hidden, d0 = f.mlp_dim0, d1 = f.mlp_dim1, LL = f.lstm_layers;
-  if (H % 128 || d0 % 128 || d1 % 128 || D % 64 || d1 > 512 || H > 1024 || d0 > 1024 || LL > HF_MAX_LAYERS) return DEER_OK;
+  if (H % 128 || d0 % 128 || d1 % 128 || D % 128 || d1 > 512 || H > 1024 || d0 > 1024 || LL > HF_MAX_LAYERS) return DEER_OK;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, c->device));
-  const int G = std::min(DEER_NUM_SMS, prop.multiProcessorCount);
-  if (H / 8 > G || 2 * d0 / 16 > G || 2 * d1 / 8 > G || !prop.cooperativeLaunch) return DEER_OK;
+  if (!prop.cooperativeLaunch) return DEER_OK;
   const int kmax = std::max(std::max(D + H, 2 * H), 2 * d0);
   const int lda = kmax + 32;                       // 64-byte skew: conflict-free 16-byte shared loads (head_fused.cuh)
   int mr = 32;
@@ -774,9 +773,40 @@ static int setup_head_fused(deer_ctx* c) {
   if ((size_t)mr * lda * 2 > 200 * 1024) return DEER_OK;
   const size_t smem = std::max((size_t)mr * lda * 2, (size_t)HF_WARPS * mr * 32 * 4);
   if (cudaFuncSetAttribute(head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return DEER_OK; }
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, head_fused_kernel, HF_THREADS, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); return DEER_OK; }
   RET(dalloc(c, reinterpret_cast<void**>(&c->hf_bar), 256, false, true));
+  // Cluster size: the largest of 8 / 4 / 1 for which the GPU can co-schedule >= 128 CTAs (one per SM: every CTA of the cooperative
+  // grid must be resident) -- checked with the occupancy query AND a dry-run launch (n = 0: the kernel returns at once).
+  const int want_cs = getenv("DEER_HEAD_CLUSTER") ? atoi(getenv("DEER_HEAD_CLUSTER")) : 8;
+  const int need = std::max(std::max(H / 8, 2 * d0 / 16), 2 * d1 / 8);
+  int G = 0, CS = 0;
+  for (int cs : {8, 4, 1}) {
+    if (cs > want_cs) continue;
+    cudaLaunchConfig_t lc = {};
+    lc.blockDim = dim3(HF_THREADS); lc.dynamicSmemBytes = smem; lc.gridDim = dim3((DEER_NUM_SMS / cs) * cs);
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+    at[1].id = cudaLaunchAttributeClusterDimension; at[1].val.clusterDim.x = cs; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = (cs > 1) ? 2 : 1;
+    int grid;
+    if (cs > 1) {
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, head_fused_kernel, &lc) != cudaSuccess) { cudaGetLastError(); continue; }
+      grid = cs * std::min(ncl, DEER_NUM_SMS / cs);
+    } else {
+      int occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, head_fused_kernel, HF_THREADS, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); continue; }
+      grid = std::min(DEER_NUM_SMS, prop.multiProcessorCount);
+    }
+    if (grid < need) continue;
+    lc.gridDim = dim3(grid); lc.stream = c->own_stream;
+    HeadFusedParams hp{};
+    hp.n_host = 0; hp.bar = c->hf_bar;
+    if (cudaLaunchKernelEx(&lc, head_fused_kernel, hp) != cudaSuccess || cudaStreamSynchronize(c->own_stream) != cudaSuccess) { cudaGetLastError(); continue; }
+    G = grid; CS = cs;
+    break;
+  }
+  if (G == 0) return DEER_OK;
+  c->hf_cluster = CS;
   c->hf_mr = mr; c->hf_lda = lda; c->hf_grid = G; c->hf_smem = smem; c->hf_ok = true;
   return DEER_OK;
 }
@@ -1152,9 +1182,10 @@ template <typename T> struct StepImpl {
       hp.cur_pose = c->cur_pose; hp.cur_grip = c->cur_grip; hp.bar = c->hf_bar; hp.n_host = n; hp.n_dev = nd; hp.dbg = g_head_dbg;
       cudaLaunchConfig_t lc = {};
       lc.gridDim = dim3(c->hf_grid); lc.blockDim = dim3(HF_THREADS); lc.dynamicSmemBytes = c->hf_smem; lc.stream = st;
-      cudaLaunchAttribute at[1];
+      cudaLaunchAttribute at[2];
       at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
-      lc.attrs = at; lc.numAttrs = 1;
+      at[1].id = cudaLaunchAttributeClusterDimension; at[1].val.clusterDim.x = c->hf_cluster; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+      lc.attrs = at; lc.numAttrs = (c->hf_cluster > 1) ? 2 : 1;
       const cudaError_t le = cudaLaunchKernelEx(&lc, head_fused_kernel, hp);
       if (le != cudaSuccess) return set_err(&c->err, DEER_E_CUDA, "head_fused launch failed: %s", cudaGetErrorString(le));
       c->stats.total++; c->stats.step++;

@@ -144,105 +144,121 @@ __device__ __forceinline__ float hf_reduce(const float* red, int mr, int ncols, 
   return s;
 }
 
-// Operand staging.  Every global load of a staging call is issued BEFORE the first shared-memory store: the compiler cannot
-// move a (generic-pointer) load above a store it may alias, so a load-convert-store loop pays one full L2 round trip per
-// iteration (measured: 15 us per LSTM layer); batched, a call pays one.
+// ---------------------------------------------------------------------------------------------------------------
+// Operand staging.  The bf16 operand of a phase ([rows, K], <= 32 rows) is needed in full by EVERY CTA (each owns a slice of the
+// output columns).  If every CTA built it from the fp32 sources itself, the grid would pull rows x K x 4 B x 148 CTAs through
+// L2 per phase (215 MB per probe at 28 rows: measured 150 us per probe, L2-bound) and normalise every row 148 times.  Instead
+// the kernel runs in thread-block CLUSTERS: CTA k of a cluster stages the rows r = k (mod cluster size) -- one L2 read,
+// one LayerNorm -- and writes the bf16 result into the shared memory of all CTAs of its cluster (st.shared::cluster); a
+// cluster barrier publishes it.  L2 traffic and LayerNorm work drop by the cluster size (8 where the GPU can co-schedule
+// enough clusters, else 4, else 1).
 //
-// one warp: LayerNorm (two-pass fp32, eps 1e-5) of TWO `len`-long fp32 rows (len % 128 == 0, <= 1024) from global memory (written
-// by other CTAs: L2-coherent loads), optional ReLU, bf16 into shared memory.  src[q] == nullptr skips a row (warp-uniform).
-__device__ __forceinline__ void hf_ln_rows_to_smem(const float* const (&src)[2], int len, const float* __restrict__ gamma,
-                                                   const float* __restrict__ beta, bool relu, bf16* const (&dst)[2], int lane) {
-  float4 v[2][8], g[8], bt[8];
+// Every global load of a staging job is issued BEFORE its first store: the compiler cannot hoist a load above a store it may
+// alias, so a load-convert-store loop would pay one L2 round trip per iteration.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hf_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t hf_mapa(uint32_t local_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void hf_st_cluster_v2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint32_t hf_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t hf_cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void hf_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// One warp, one job: `len` (<= 1024, % 128 == 0) fp32 values at src (global; may have been written by other CTAs: L2-coherent
+// loads) -> [LayerNorm over exactly these len values (two-pass fp32, eps 1e-5) (+ReLU) when gamma != nullptr] -> bf16 -> byte
+// offset `off` of the operand buffer of every CTA of the cluster (peer[d] = cluster address of that CTA's buffer).
+__device__ __forceinline__ void hf_stage_job(const float* src, int len, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                             bool relu, uint32_t off, const uint32_t (&peer)[8], int cs, int lane) {
+  float4 v[8], g[8], bt[8];
   const int nv = len >> 7;
+  const bool ln = gamma != nullptr;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int j = (lane + 32 * i) * 4;
-#pragma unroll
-    for (int q = 0; q < 2; ++q)
-      v[q][i] = (src[q] != nullptr && i < nv) ? __ldcg(reinterpret_cast<const float4*>(src[q] + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    g[i] = (i < nv) ? __ldg(reinterpret_cast<const float4*>(gamma + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    bt[i] = (i < nv) ? __ldg(reinterpret_cast<const float4*>(beta + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[i] = (i < nv) ? __ldcg(reinterpret_cast<const float4*>(src + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    g[i] = (ln && i < nv) ? __ldg(reinterpret_cast<const float4*>(gamma + j)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    bt[i] = (ln && i < nv) ? __ldg(reinterpret_cast<const float4*>(beta + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  const float inv_len = 1.0f / static_cast<float>(len);
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    if (src[q] == nullptr) continue;
+  float mean = 0.0f, rstd = 1.0f;
+  if (ln) {
+    const float inv_len = 1.0f / static_cast<float>(len);
     float s = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += (v[q][i].x + v[q][i].y) + (v[q][i].z + v[q][i].w);
-    const float mean = warp_sum(s) * inv_len;
+    for (int i = 0; i < 8; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    mean = warp_sum(s) * inv_len;
     float sq = 0.0f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (i < nv) {
-        const float a = v[q][i].x - mean, b = v[q][i].y - mean, c = v[q][i].z - mean, d = v[q][i].w - mean;
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
         sq += (a * a + b * b) + (c * c + d * d);
       }
     }
-    const float rstd = rsqrtf(warp_sum(sq) * inv_len + 1e-5f);
+    rstd = rsqrtf(warp_sum(sq) * inv_len + 1e-5f);
+  }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i < nv) {
-        float4 y;
-        y.x = (v[q][i].x - mean) * rstd * g[i].x + bt[i].x; y.y = (v[q][i].y - mean) * rstd * g[i].y + bt[i].y;
-        y.z = (v[q][i].z - mean) * rstd * g[i].z + bt[i].z; y.w = (v[q][i].w - mean) * rstd * g[i].w + bt[i].w;
+  for (int i = 0; i < 8; ++i) {
+    if (i < nv) {
+      float4 y = v[i];
+      if (ln) {
+        y.x = (v[i].x - mean) * rstd * g[i].x + bt[i].x; y.y = (v[i].y - mean) * rstd * g[i].y + bt[i].y;
+        y.z = (v[i].z - mean) * rstd * g[i].z + bt[i].z; y.w = (v[i].w - mean) * rstd * g[i].w + bt[i].w;
         if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-        uint2 o; o.x = pack_bf16x2(y.x, y.y); o.y = pack_bf16x2(y.z, y.w);
-        *reinterpret_cast<uint2*>(dst[q] + (lane + 32 * i) * 4) = o;
       }
+      const uint32_t lo = pack_bf16x2(y.x, y.y), hi = pack_bf16x2(y.z, y.w);
+      const uint32_t o = off + static_cast<uint32_t>((lane + 32 * i) * 8);
+#pragma unroll
+      for (int d = 0; d < 8; ++d)
+        if (d < cs) hf_st_cluster_v2(peer[d] + o, lo, hi);
     }
   }
 }
-// one warp: FOUR fp32 rows (global, possibly written by other CTAs) -> bf16 shared memory, len % 4 == 0; 1024 elements of every row
-// are in flight per pass
-__device__ __forceinline__ void hf_copy_rows_to_smem(const float* const (&src)[4], int len, bf16* const (&dst)[4], int lane) {
-  for (int j0 = 0; j0 < len; j0 += 1024) {
-    float4 v[4][8];
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int j = j0 + (lane + 32 * i) * 4;
-        v[q][i] = (src[q] != nullptr && j < len) ? __ldcg(reinterpret_cast<const float4*>(src[q] + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int j = j0 + (lane + 32 * i) * 4;
-        if (src[q] != nullptr && j < len) {
-          uint2 o; o.x = pack_bf16x2(v[q][i].x, v[q][i].y); o.y = pack_bf16x2(v[q][i].z, v[q][i].w);
-          *reinterpret_cast<uint2*>(dst[q] + j) = o;
-        }
-      }
-  }
-}
-__device__ __forceinline__ void hf_zero_row(bf16* row, int len, int lane) {
-  for (int j = lane * 8; j < len; j += 256) *reinterpret_cast<uint4*>(row + j) = make_uint4(0u, 0u, 0u, 0u);
-}
+
+#define HF_MARK(i)                                                                                            \
+  do {                                                                                                        \
+    if (p.dbg != nullptr && cta == 0 && threadIdx.x == 0) {                                                   \
+      unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); p.dbg[(i)] = (long long)_t; \
+    }                                                                                                         \
+  } while (0)
 
 __global__ void __launch_bounds__(HF_THREADS, 1)
 head_fused_kernel(const HeadFusedParams p) {
   extern __shared__ __align__(16) uint8_t hf_smem[];
   bf16* A_s = reinterpret_cast<bf16*>(hf_smem);
   float* red = reinterpret_cast<float*>(hf_smem);          // aliases A_s once a GEMM has consumed it
+  __shared__ int s_slot[32];
   const int n = dyn_rows(p.n_host, p.n_dev, 1);
-  if (n <= 0) return;                                      // uniform over the grid: nobody touches the barrier
+  if (n <= 0) return;                                      // uniform over the grid: nobody touches a barrier
   const int G = gridDim.x, cta = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int H = p.H, D = p.D, LL = p.LL, d0 = p.d0, d1 = p.d1, lda = p.lda, mr = p.mr;
   const bool two_m = n > 16;
   const int rows_used = two_m ? 32 : 16;
+  const int cs = static_cast<int>(hf_cluster_size());      // 1, 4 or 8 (divides 16)
+  const int crank = static_cast<int>(hf_cluster_rank());
+  const int my_rows = rows_used / cs;                      // rows this CTA stages for its cluster: r = crank + cs * i
+  uint32_t peer[8];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) peer[d] = hf_mapa(hf_smem_u32(A_s), static_cast<uint32_t>(d < cs ? d : 0));
   const unsigned long long per_launch = static_cast<unsigned long long>(G) * (LL + 3);
   unsigned long long bar_target = 0;
-  if (threadIdx.x == 0) bar_target = (ld_acquire_u64(p.bar) / per_launch) * per_launch;     // see the header: < G arrivals of this launch so far
+  if (threadIdx.x == 0) bar_target = (ld_acquire_u64(p.bar) / per_launch) * per_launch;     // < G arrivals of this launch so far
   int n_bar = 0;
   const int nu = H / 8;                                    // LSTM work items: 8 hidden units (x 4 gates = 32 weight rows)
   const int n1 = 2 * d0 / 16;                              // MLP1 items: 16 columns
   const int n2 = 2 * d1 / 8;                               // MLP2 items: 8 columns
+  if (threadIdx.x < 32) s_slot[threadIdx.x] = (threadIdx.x < n) ? p.slot[threadIdx.x] : 0;
 
-  if (p.dbg != nullptr && cta == 0 && threadIdx.x == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); p.dbg[0] = (long long)_t; }
+  HF_MARK(0);
   // ---- L2 prefetch of every weight row this CTA will stream, in phase order (82 MB over the grid; L2 holds 126 MB)
   for (int l = 0; l < LL; ++l) {
     const int K = (l == 0 ? D : H) + H;
@@ -288,40 +304,55 @@ head_fused_kernel(const HeadFusedParams p) {
   }
 #define HF_BARRIER()                                                          \
   do {                                                                        \
-    if (p.dbg != nullptr && cta == 0 && threadIdx.x == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); p.dbg[2 * n_bar + 1] = (long long)_t; } \
+    HF_MARK(2 * n_bar + 1);                                                   \
     ++n_bar;                                                                  \
     hf_grid_barrier(p.bar, bar_target + static_cast<unsigned long long>(n_bar) * G); \
-    if (p.dbg != nullptr && cta == 0 && threadIdx.x == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); p.dbg[2 * n_bar] = (long long)_t; } \
+    HF_MARK(2 * n_bar);                                                       \
+  } while (0)
+  // rows >= n of the operand are zero: every CTA clears its own copy (peers only ever write rows < n)
+#define HF_ZERO_TAIL(KLEN)                                                                               \
+  do {                                                                                                   \
+    for (int r = n + warp; r < rows_used; r += HF_WARPS)                                                 \
+      for (int j = lane * 8; j < (KLEN); j += 256) *reinterpret_cast<uint4*>(A_s + static_cast<size_t>(r) * lda + j) = make_uint4(0u, 0u, 0u, 0u); \
   } while (0)
   HF_BARRIER();
 
   // ---- LSTM layers
   for (int l = 0; l < LL; ++l) {
     const int in = (l == 0) ? D : H, K = in + H;
-    const bool has_work = cta < nu;
-    if (has_work) {
-      // operand [rows, in | H]: layer input (pooled feature / LayerNorm of the previous layer's h) | carried h of this layer
-      // (a warp owns rows warp, warp + 8, warp + 16, warp + 24)
-      const float* hsrc[4]; const float* xsrc[4]; bf16* dst[4]; bf16* dsth[4];
+    // this thread's cell of the layer's epilogue: bias and carried c are fetched now, off the critical path
+    const int e_r = threadIdx.x >> 3, e_u = threadIdx.x & 7;
+    const bool e_on = (cta < nu) && e_r < n;
+    float e_b[4] = {0.f, 0.f, 0.f, 0.f}, e_c = 0.0f;
+    if (e_on) {
+      const int j = cta * 8 + e_u;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int r = warp + 8 * q;
-        dst[q] = A_s + static_cast<size_t>(r) * lda;
-        dsth[q] = dst[q] + in;
-        hsrc[q] = (r < n) ? p.h_state + (static_cast<size_t>(p.slot[r]) * LL + l) * H : nullptr;
-        xsrc[q] = (r < n) ? ((l == 0) ? p.pooled + static_cast<size_t>(r) * D : p.cand_h + (static_cast<size_t>(l - 1) * p.nstride + r) * H) : nullptr;
-        if (r >= n && r < rows_used) hf_zero_row(dst[q], K, lane);
-      }
-      hf_copy_rows_to_smem(hsrc, H, dsth, lane);
-      if (l == 0) hf_copy_rows_to_smem(xsrc, D, dst, lane);
-      else {
-        const float* s01[2] = {xsrc[0], xsrc[1]}; bf16* d01[2] = {dst[0], dst[1]};
-        const float* s23[2] = {xsrc[2], xsrc[3]}; bf16* d23[2] = {dst[2], dst[3]};
-        hf_ln_rows_to_smem(s01, H, p.ln_g[l - 1], p.ln_b[l - 1], false, d01, lane);
-        if (two_m) hf_ln_rows_to_smem(s23, H, p.ln_g[l - 1], p.ln_b[l - 1], false, d23, lane);
-      }
+      for (int q = 0; q < 4; ++q) e_b[q] = __ldg(p.b_sum[l] + q * H + j);
+      e_c = p.c_state[(static_cast<size_t>(s_slot[e_r]) * LL + l) * H + j];
     }
-    __syncthreads();
+    // operand [rows, in | H]: layer input (pooled feature / LayerNorm of the previous layer's h) | carried h of this layer.
+    // jobs of this CTA: (row i, part): parts = in / 1024 pooled pieces (l == 0) or one LayerNorm row, then the h row
+    {
+      const int xparts = (l == 0) ? (D + 1023) / 1024 : 1;
+      const int njobs = my_rows * (xparts + 1);
+      for (int jb = warp; jb < njobs; jb += HF_WARPS) {
+        const int i = jb / (xparts + 1), part = jb % (xparts + 1);
+        const int r = crank + cs * i;
+        if (r >= n) continue;                              // warp-uniform
+        const uint32_t row_off = static_cast<uint32_t>(r) * lda * 2;
+        if (part == xparts) {
+          hf_stage_job(p.h_state + (static_cast<size_t>(s_slot[r]) * LL + l) * H, H, nullptr, nullptr, false, row_off + in * 2, peer, cs, lane);
+        } else if (l == 0) {
+          const int c0 = part * 1024, len = min(1024, D - c0);
+          hf_stage_job(p.pooled + static_cast<size_t>(r) * D + c0, len, nullptr, nullptr, false, row_off + c0 * 2, peer, cs, lane);
+        } else {
+          hf_stage_job(p.cand_h + (static_cast<size_t>(l - 1) * p.nstride + r) * H, H, p.ln_g[l - 1], p.ln_b[l - 1], false, row_off, peer, cs, lane);
+        }
+      }
+      HF_ZERO_TAIL(K);
+    }
+    hf_cluster_sync();
+    if (l == 1) HF_MARK(16);
     for (int it = cta; it < nu; it += G) {
       const int j0 = it * 8;
       float acc[2][4][4];
@@ -336,22 +367,22 @@ head_fused_kernel(const HeadFusedParams p) {
       for (int q = 0; q < 4; ++q) wp[q] = p.w_cat[l] + static_cast<size_t>(q * H + j0 + g) * K + t * 8;
       hf_skinny_gemm<4>(A_s + static_cast<size_t>(g) * lda + t * 8, lda, two_m, wp, K, warp, acc);
       __syncthreads();                                     // every warp is done reading A_s (red aliases it)
+      if (l == 1) HF_MARK(17);
       hf_store_partials<4>(red, mr, two_m, warp, lane, acc);
       __syncthreads();
-      // LSTM cell (gate order i, f, g, o) for (row, unit) pairs
-      for (int idx = threadIdx.x; idx < n * 8; idx += HF_THREADS) {
-        const int r = idx >> 3, u = idx & 7, j = j0 + u;
-        const float gi = hf_reduce(red, mr, 32, r, u) + p.b_sum[l][j];
-        const float gf = hf_reduce(red, mr, 32, r, 8 + u) + p.b_sum[l][H + j];
-        const float gg = hf_reduce(red, mr, 32, r, 16 + u) + p.b_sum[l][2 * H + j];
-        const float go = hf_reduce(red, mr, 32, r, 24 + u) + p.b_sum[l][3 * H + j];
-        const float cp = p.c_state[(static_cast<size_t>(p.slot[r]) * LL + l) * H + j];
-        const float c2 = sigmoidf_(gf) * cp + sigmoidf_(gi) * tanhf(gg);
+      // LSTM cell (gate order i, f, g, o): thread = (row, unit)
+      if (e_on) {
+        const int j = j0 + e_u;
+        const float gi = hf_reduce(red, mr, 32, e_r, e_u) + e_b[0];
+        const float gf = hf_reduce(red, mr, 32, e_r, 8 + e_u) + e_b[1];
+        const float gg = hf_reduce(red, mr, 32, e_r, 16 + e_u) + e_b[2];
+        const float go = hf_reduce(red, mr, 32, e_r, 24 + e_u) + e_b[3];
+        const float c2 = sigmoidf_(gf) * e_c + sigmoidf_(gi) * tanhf(gg);
         const float h2 = sigmoidf_(go) * tanhf(c2);
-        p.cand_c[(static_cast<size_t>(l) * p.nstride + r) * H + j] = c2;
-        p.cand_h[(static_cast<size_t>(l) * p.nstride + r) * H + j] = h2;
+        p.cand_c[(static_cast<size_t>(l) * p.nstride + e_r) * H + j] = c2;
+        p.cand_h[(static_cast<size_t>(l) * p.nstride + e_r) * H + j] = h2;
       }
-      __syncthreads();
+      if (l == 1) HF_MARK(18);
       // (a second item of the same layer would need A_s again: only reachable when H / 8 > gridDim.x, which the host excludes)
     }
     HF_BARRIER();
@@ -359,21 +390,14 @@ head_fused_kernel(const HeadFusedParams p) {
 
   // ---- MLP layer 1 of both heads: [n, H] x [2*d0, H]^T, operand = LayerNorm of the last LSTM layer's h
   {
-    if (cta < n1) {
-      const float* src[4]; bf16* dst[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int r = warp + 8 * q;
-        dst[q] = A_s + static_cast<size_t>(r) * lda;
-        src[q] = (r < n) ? p.cand_h + (static_cast<size_t>(LL - 1) * p.nstride + r) * H : nullptr;
-        if (r >= n && r < rows_used) hf_zero_row(dst[q], H, lane);
-      }
-      const float* s01[2] = {src[0], src[1]}; bf16* d01[2] = {dst[0], dst[1]};
-      const float* s23[2] = {src[2], src[3]}; bf16* d23[2] = {dst[2], dst[3]};
-      hf_ln_rows_to_smem(s01, H, p.ln_g[LL - 1], p.ln_b[LL - 1], false, d01, lane);
-      if (two_m) hf_ln_rows_to_smem(s23, H, p.ln_g[LL - 1], p.ln_b[LL - 1], false, d23, lane);
+    for (int i = warp; i < my_rows; i += HF_WARPS) {
+      const int r = crank + cs * i;
+      if (r >= n) continue;
+      hf_stage_job(p.cand_h + (static_cast<size_t>(LL - 1) * p.nstride + r) * H, H, p.ln_g[LL - 1], p.ln_b[LL - 1], false,
+                   static_cast<uint32_t>(r) * lda * 2, peer, cs, lane);
     }
-    __syncthreads();
+    HF_ZERO_TAIL(H);
+    hf_cluster_sync();
     for (int it = cta; it < n1; it += G) {
       float acc[2][2][4];
 #pragma unroll
@@ -391,32 +415,22 @@ head_fused_kernel(const HeadFusedParams p) {
       __syncthreads();
       for (int idx = threadIdx.x; idx < n * 16; idx += HF_THREADS) {
         const int r = idx >> 4, cc = idx & 15, col = it * 16 + cc;
-        p.mlp1[static_cast<size_t>(r) * 2 * d0 + col] = hf_reduce(red, mr, 16, r, cc) + p.b_mlp1[col];
+        p.mlp1[static_cast<size_t>(r) * 2 * d0 + col] = hf_reduce(red, mr, 16, r, cc) + __ldg(p.b_mlp1 + col);
       }
-      __syncthreads();
     }
     HF_BARRIER();
   }
 
   // ---- MLP layer 2: per head [n, d0] x [d1, d0]^T, operand = ReLU(LayerNorm(mlp1 half))
   {
-    if (cta < n2) {
-      for (int head = 0; head < 2; ++head) {               // a warp owns rows warp + 8q; per head, two rows per call
-        const float* src[4]; bf16* dst[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int r = warp + 8 * q;
-          dst[q] = A_s + static_cast<size_t>(r) * lda + head * d0;
-          src[q] = (r < n) ? p.mlp1 + static_cast<size_t>(r) * 2 * d0 + head * d0 : nullptr;
-          if (r >= n && r < rows_used) hf_zero_row(dst[q], d0, lane);
-        }
-        const float* s01[2] = {src[0], src[1]}; bf16* d01[2] = {dst[0], dst[1]};
-        const float* s23[2] = {src[2], src[3]}; bf16* d23[2] = {dst[2], dst[3]};
-        hf_ln_rows_to_smem(s01, d0, p.g_mlp1 + head * d0, p.be_mlp1 + head * d0, true, d01, lane);
-        if (two_m) hf_ln_rows_to_smem(s23, d0, p.g_mlp1 + head * d0, p.be_mlp1 + head * d0, true, d23, lane);
-      }
+    for (int jb = warp; jb < 2 * my_rows; jb += HF_WARPS) {
+      const int r = crank + cs * (jb >> 1), head = jb & 1;
+      if (r >= n) continue;
+      hf_stage_job(p.mlp1 + static_cast<size_t>(r) * 2 * d0 + head * d0, d0, p.g_mlp1 + head * d0, p.be_mlp1 + head * d0, true,
+                   static_cast<uint32_t>(r) * lda * 2 + head * d0 * 2, peer, cs, lane);
     }
-    __syncthreads();
+    HF_ZERO_TAIL(2 * d0);
+    hf_cluster_sync();
     for (int it = cta; it < n2; it += G) {
       const int head = it / (d1 / 8), c0 = (it % (d1 / 8)) * 8;
       float acc[2][1][4];
@@ -432,9 +446,8 @@ head_fused_kernel(const HeadFusedParams p) {
       __syncthreads();
       for (int idx = threadIdx.x; idx < n * 8; idx += HF_THREADS) {
         const int r = idx >> 3, cc = idx & 7, col = head * d1 + c0 + cc;
-        p.mlp2[static_cast<size_t>(r) * 2 * d1 + col] = hf_reduce(red, mr, 8, r, cc) + p.b_mlp2[col];
+        p.mlp2[static_cast<size_t>(r) * 2 * d1 + col] = hf_reduce(red, mr, 8, r, cc) + __ldg(p.b_mlp2 + col);
       }
-      __syncthreads();
     }
     HF_BARRIER();
   }
@@ -447,30 +460,28 @@ head_fused_kernel(const HeadFusedParams p) {
       const float* gam = p.g_mlp2 + head * d1;
       const float* bet = p.be_mlp2 + head * d1;
       const float* w = head ? p.w3_grip : p.w3_pose + static_cast<size_t>(warp) * d1;
-      float v[16];
-      const int nv = (d1 + 127) / 128 * 4;                 // values per lane, lane-strided by 32
+      float v[16], gv[16], bv[16], wv[16];
       float s = 0.0f;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int j = lane + 32 * i;
-        v[i] = (i < nv && j < d1) ? __ldcg(src + j) : 0.0f;
+        const bool on = j < d1;
+        v[i] = on ? __ldcg(src + j) : 0.0f;
+        gv[i] = on ? __ldg(gam + j) : 0.0f; bv[i] = on ? __ldg(bet + j) : 0.0f; wv[i] = on ? __ldg(w + j) : 0.0f;
         s += v[i];
       }
       const float mean = warp_sum(s) / static_cast<float>(d1);
       float q = 0.0f;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const int j = lane + 32 * i;
-        const float d = (i < nv && j < d1) ? v[i] - mean : 0.0f;
+        const float d = (lane + 32 * i < d1) ? v[i] - mean : 0.0f;
         q += d * d;
       }
       const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(d1) + 1e-5f);
       float acc = 0.0f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int j = lane + 32 * i;
-        if (i < nv && j < d1) acc += fmaxf((v[i] - mean) * rstd * gam[j] + bet[j], 0.0f) * w[j];
-      }
+      for (int i = 0; i < 16; ++i)
+        if (lane + 32 * i < d1) acc += fmaxf((v[i] - mean) * rstd * gv[i] + bv[i], 0.0f) * wv[i];
       acc = warp_sum(acc);
       if (lane == 0) {
         if (head) p.cur_grip[r] = sigmoidf_(acc + p.b3_grip[0]);
@@ -478,7 +489,10 @@ head_fused_kernel(const HeadFusedParams p) {
       }
     }
   }
-  if (p.dbg != nullptr && cta == 0 && threadIdx.x == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); p.dbg[2 * n_bar + 1] = (long long)_t; }
+  HF_MARK(2 * n_bar + 1);
   // every launch adds exactly gridDim.x * (LL + 3) barrier arrivals (n_bar == LL + 3 here)
+  hf_cluster_sync();                                       // no CTA of a cluster exits while a peer could still address its shared memory
 #undef HF_BARRIER
+#undef HF_ZERO_TAIL
+#undef HF_MARK
 }

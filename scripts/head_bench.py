@@ -15,10 +15,11 @@ dev = torch.device("cuda", 0)
 S = 32
 sd = list(synth_state_items(cfg, 0))
 res = {}
+quick = "--quick" in sys.argv          # fused path only (cluster-size A/B via DEER_HEAD_CLUSTER)
 for B in (28, 1):
     fr = [(synth_frames(cfg, B, 1000 + i, dev), synth_frames(cfg, B, 5000 + i, dev)) for i in range(4)]
     ids = synth_instruction_ids(cfg, B, S, seed=2000).to(dev)
-    for fused in (1, 0):
+    for fused in ((1,) if quick else (1, 0)):
         os.environ["DEER_HEAD_FUSED"] = str(fused)
         eng = DeerEngine(cfg, max_batch=B, max_slots=B, max_seq=S, device=0, precision="bf16")
         eng.load_state_dict(sd)
@@ -62,6 +63,9 @@ for B in (28, 1):
                 wait = (t[2 * k + 2] - t[2 * k + 1]) if k < 7 else 0
                 line.append(f"{names[k]} {work / 1e3:.1f}+{wait / 1e3:.1f}us")
             print(f"  head probe timeline (CTA 0; work + barrier wait): {', '.join(line)}; total {(t[15] - t[0]) / 1e3:.1f} us", flush=True)
+            f = list(buf)[16:19]
+            print(f"  lstm1 breakdown: stage+cluster sync {(f[0] - t[4]) / 1e3:.1f} us, gemm {(f[1] - f[0]) / 1e3:.1f} us, reduce+cell {(f[2] - f[1]) / 1e3:.1f} us "
+                  f"(cluster size {os.environ.get('DEER_HEAD_CLUSTER', '8')})", flush=True)
             res[f"B{B}_head_timeline_ns"] = [int(x - t[0]) for x in t]
             lib.deer_head_debug(0, None, 0)
         eng.close()
