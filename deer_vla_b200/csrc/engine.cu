@@ -762,7 +762,7 @@ static int setup_head_fused(deer_ctx* c) {
   if (c->dtype != 0 || f.gemm_impl != DEER_GEMM_TCGEN05) return DEER_OK;
   if (!f.lstm_layernorm || !f.mlp_layernorm || f.mlp_dim2 > 0) return DEER_OK;
   const int D = f.d_model, H = f.lstm_hidden, d0 = f.mlp_dim0, d1 = f.mlp_dim1, LL = f.lstm_layers;
-  if (H % 128 || d0 % 128 || d1 % 128 || D % 128 || d1 > 512 || H > 1024 || d0 > 1024 || LL > HF_MAX_LAYERS) return DEER_OK;
+  if (H % 256 || d0 % 256 || d1 % 128 || D % 256 || d1 > 512 || H > 1024 || d0 > 1024 || LL > HF_MAX_LAYERS) return DEER_OK;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, c->device));
   if (!prop.cooperativeLaunch) return DEER_OK;

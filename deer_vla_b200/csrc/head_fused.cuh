@@ -83,39 +83,49 @@ __device__ __forceinline__ void hf_grid_barrier(unsigned long long* bar, unsigne
   __syncthreads();
 }
 
-// acc[mt][nt][4] += A_s[rows, k] * W[wrow(nt), k] over this warp's interleaved 32-wide k chunks.
+// acc[mt][nt][4] += A_s[rows, k] * W[wrow(nt), k] over this warp's interleaved 32-wide k chunks, in batches of four chunks.
 // wp[nt]: this thread's weight row pointer (row = column (lane >> 2) of n-tile nt), already offset by (lane & 3) * 8.
 // as: this thread's operand pointer A_s + (lane >> 2) * lda + (lane & 3) * 8 (+ a column offset of the operand).
+// The FIRST batch of a phase is loaded into registers before the grid barrier and the operand staging (the weights do not
+// depend on them), so its HBM latency is hidden behind both.
 template <int NT>
-__device__ __forceinline__ void hf_skinny_gemm(const bf16* as, int lda, bool two_m, const bf16* (&wp)[NT], int K, int warp,
-                                               float (&acc)[2][NT][4]) {
-  const int kc = K >> 5;                                  // 32-wide chunks
-  for (int c0 = warp; c0 < kc; c0 += 4 * HF_WARPS) {
-    uint4 b[4][NT];
+__device__ __forceinline__ void hf_load_batch(uint4 (&b)[4][NT], const bf16* (&wp)[NT], int c0, int kc) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int c = c0 + u * HF_WARPS;
+  for (int u = 0; u < 4; ++u) {
+    const int c = c0 + u * HF_WARPS;
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) b[u][nt] = (c < kc) ? ldg_nc_v4(wp[nt] + c * 32) : make_uint4(0u, 0u, 0u, 0u);
-    }
+    for (int nt = 0; nt < NT; ++nt) b[u][nt] = (c < kc) ? ldg_nc_v4(wp[nt] + c * 32) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+template <int NT>
+__device__ __forceinline__ void hf_mma_batch(const bf16* as, int lda, bool two_m, const uint4 (&b)[4][NT], int c0, int kc, float (&acc)[2][NT][4]) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int c = c0 + u * HF_WARPS;
-      if (c < kc) {
+  for (int u = 0; u < 4; ++u) {
+    const int c = c0 + u * HF_WARPS;
+    if (c < kc) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          if (mt == 0 || two_m) {
-            const uint4 lo = *reinterpret_cast<const uint4*>(as + (mt * 16) * lda + c * 32);
-            const uint4 hi = *reinterpret_cast<const uint4*>(as + (mt * 16 + 8) * lda + c * 32);
+      for (int mt = 0; mt < 2; ++mt) {
+        if (mt == 0 || two_m) {
+          const uint4 lo = *reinterpret_cast<const uint4*>(as + (mt * 16) * lda + c * 32);
+          const uint4 hi = *reinterpret_cast<const uint4*>(as + (mt * 16 + 8) * lda + c * 32);
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-              mma_bf16_16816(acc[mt][nt], lo.x, hi.x, lo.y, hi.y, b[u][nt].x, b[u][nt].y);
-              mma_bf16_16816(acc[mt][nt], lo.z, hi.z, lo.w, hi.w, b[u][nt].z, b[u][nt].w);
-            }
+          for (int nt = 0; nt < NT; ++nt) {
+            mma_bf16_16816(acc[mt][nt], lo.x, hi.x, lo.y, hi.y, b[u][nt].x, b[u][nt].y);
+            mma_bf16_16816(acc[mt][nt], lo.z, hi.z, lo.w, hi.w, b[u][nt].z, b[u][nt].w);
           }
         }
       }
     }
+  }
+}
+// `b` holds the batch at c0 = warp (already loaded)
+template <int NT>
+__device__ __forceinline__ void hf_skinny_gemm(const bf16* as, int lda, bool two_m, const bf16* (&wp)[NT], int K, int warp,
+                                               uint4 (&b)[4][NT], float (&acc)[2][NT][4]) {
+  const int kc = K >> 5;                                  // 32-wide chunks
+  for (int c0 = warp; c0 < kc; c0 += 4 * HF_WARPS) {
+    if (c0 != warp) hf_load_batch<NT>(b, wp, c0, kc);
+    hf_mma_batch<NT>(as, lda, two_m, b, c0, kc, acc);
   }
 }
 
@@ -172,20 +182,27 @@ __device__ __forceinline__ void hf_cluster_sync() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// One warp, one job: `len` (<= 1024, % 128 == 0) fp32 values at src (global; may have been written by other CTAs: L2-coherent
+__device__ __forceinline__ void hf_st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// One warp, one job: `len` (<= 1024, % 256 == 0) fp32 values at src (global; may have been written by other CTAs: L2-coherent
 // loads) -> [LayerNorm over exactly these len values (two-pass fp32, eps 1e-5) (+ReLU) when gamma != nullptr] -> bf16 -> byte
-// offset `off` of the operand buffer of every CTA of the cluster (peer[d] = cluster address of that CTA's buffer).
+// offset `off` of the operand buffer of every CTA of the cluster (peer[d] = cluster address of that CTA's buffer).  A lane owns
+// 8 consecutive values per 256-wide group, so a remote store carries 16 bytes.
 __device__ __forceinline__ void hf_stage_job(const float* src, int len, const float* __restrict__ gamma, const float* __restrict__ beta,
                                              bool relu, uint32_t off, const uint32_t (&peer)[8], int cs, int lane) {
   float4 v[8], g[8], bt[8];
-  const int nv = len >> 7;
+  const int ng = len >> 8;                                 // 256-wide groups; v[2i], v[2i+1] = the lane's 8 values of group i
   const bool ln = gamma != nullptr;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int j = (lane + 32 * i) * 4;
-    v[i] = (i < nv) ? __ldcg(reinterpret_cast<const float4*>(src + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    g[i] = (ln && i < nv) ? __ldg(reinterpret_cast<const float4*>(gamma + j)) : make_float4(1.f, 1.f, 1.f, 1.f);
-    bt[i] = (ln && i < nv) ? __ldg(reinterpret_cast<const float4*>(beta + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = i * 256 + lane * 8 + h * 4;
+      v[2 * i + h] = (i < ng) ? __ldcg(reinterpret_cast<const float4*>(src + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      g[2 * i + h] = (ln && i < ng) ? __ldg(reinterpret_cast<const float4*>(gamma + j)) : make_float4(1.f, 1.f, 1.f, 1.f);
+      bt[2 * i + h] = (ln && i < ng) ? __ldg(reinterpret_cast<const float4*>(beta + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   float mean = 0.0f, rstd = 1.0f;
   if (ln) {
@@ -197,7 +214,7 @@ __device__ __forceinline__ void hf_stage_job(const float* src, int len, const fl
     float sq = 0.0f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      if (i < nv) {
+      if ((i >> 1) < ng) {
         const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
         sq += (a * a + b * b) + (c * c + d * d);
       }
@@ -205,19 +222,24 @@ __device__ __forceinline__ void hf_stage_job(const float* src, int len, const fl
     rstd = rsqrtf(warp_sum(sq) * inv_len + 1e-5f);
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (i < nv) {
-      float4 y = v[i];
-      if (ln) {
-        y.x = (v[i].x - mean) * rstd * g[i].x + bt[i].x; y.y = (v[i].y - mean) * rstd * g[i].y + bt[i].y;
-        y.z = (v[i].z - mean) * rstd * g[i].z + bt[i].z; y.w = (v[i].w - mean) * rstd * g[i].w + bt[i].w;
-        if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+  for (int i = 0; i < 4; ++i) {
+    if (i < ng) {
+      uint32_t w[4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = 2 * i + h;
+        float4 y = v[k];
+        if (ln) {
+          y.x = (v[k].x - mean) * rstd * g[k].x + bt[k].x; y.y = (v[k].y - mean) * rstd * g[k].y + bt[k].y;
+          y.z = (v[k].z - mean) * rstd * g[k].z + bt[k].z; y.w = (v[k].w - mean) * rstd * g[k].w + bt[k].w;
+          if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+        }
+        w[2 * h] = pack_bf16x2(y.x, y.y); w[2 * h + 1] = pack_bf16x2(y.z, y.w);
       }
-      const uint32_t lo = pack_bf16x2(y.x, y.y), hi = pack_bf16x2(y.z, y.w);
-      const uint32_t o = off + static_cast<uint32_t>((lane + 32 * i) * 8);
+      const uint32_t o = off + static_cast<uint32_t>((i * 256 + lane * 8) * 2);
 #pragma unroll
       for (int d = 0; d < 8; ++d)
-        if (d < cs) hf_st_cluster_v2(peer[d] + o, lo, hi);
+        if (d < cs) hf_st_cluster_v4(peer[d] + o, w[0], w[1], w[2], w[3]);
     }
   }
 }
@@ -315,8 +337,17 @@ head_fused_kernel(const HeadFusedParams p) {
     for (int r = n + warp; r < rows_used; r += HF_WARPS)                                                 \
       for (int j = lane * 8; j < (KLEN); j += 256) *reinterpret_cast<uint4*>(A_s + static_cast<size_t>(r) * lda + j) = make_uint4(0u, 0u, 0u, 0u); \
   } while (0)
+  // weight pointers / first batches: loaded ahead of the barrier that precedes their phase
+  uint4 pre4[4][4];
+  const bf16* wp4[4];
+  const bool lstm_on = cta < nu;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) wp4[q] = p.w_cat[0] + static_cast<size_t>(q * H + (lstm_on ? cta : 0) * 8 + g) * (D + H) + t * 8;
+  if (lstm_on) hf_load_batch<4>(pre4, wp4, warp, (D + H) >> 5);
   HF_BARRIER();
 
+  uint4 pre2[4][2];
+  const bf16* wp2[2];
   // ---- LSTM layers
   for (int l = 0; l < LL; ++l) {
     const int in = (l == 0) ? D : H, K = in + H;
@@ -353,8 +384,8 @@ head_fused_kernel(const HeadFusedParams p) {
     }
     hf_cluster_sync();
     if (l == 1) HF_MARK(16);
-    for (int it = cta; it < nu; it += G) {
-      const int j0 = it * 8;
+    if (lstm_on) {
+      const int j0 = cta * 8;
       float acc[2][4][4];
 #pragma unroll
       for (int a = 0; a < 2; ++a)
@@ -362,10 +393,7 @@ head_fused_kernel(const HeadFusedParams p) {
         for (int b = 0; b < 4; ++b)
 #pragma unroll
           for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.0f;
-      const bf16* wp[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) wp[q] = p.w_cat[l] + static_cast<size_t>(q * H + j0 + g) * K + t * 8;
-      hf_skinny_gemm<4>(A_s + static_cast<size_t>(g) * lda + t * 8, lda, two_m, wp, K, warp, acc);
+      hf_skinny_gemm<4>(A_s + static_cast<size_t>(g) * lda + t * 8, lda, two_m, wp4, K, warp, pre4, acc);
       __syncthreads();                                     // every warp is done reading A_s (red aliases it)
       if (l == 1) HF_MARK(17);
       hf_store_partials<4>(red, mr, two_m, warp, lane, acc);
@@ -383,11 +411,22 @@ head_fused_kernel(const HeadFusedParams p) {
         p.cand_h[(static_cast<size_t>(l) * p.nstride + e_r) * H + j] = h2;
       }
       if (l == 1) HF_MARK(18);
-      // (a second item of the same layer would need A_s again: only reachable when H / 8 > gridDim.x, which the host excludes)
+    }
+    // next phase's first weight batch (the host guarantees one work item per CTA and phase: H / 8, 2*d0 / 16, 2*d1 / 8 <= gridDim.x)
+    if (l + 1 < LL) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) wp4[q] = p.w_cat[l + 1] + static_cast<size_t>(q * H + (lstm_on ? cta : 0) * 8 + g) * (2 * H) + t * 8;
+      if (lstm_on) hf_load_batch<4>(pre4, wp4, warp, (2 * H) >> 5);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) wp2[q] = p.w_mlp1 + static_cast<size_t>((cta < n1 ? cta : 0) * 16 + q * 8 + g) * H + t * 8;
+      if (cta < n1) hf_load_batch<2>(pre2, wp2, warp, H >> 5);
     }
     HF_BARRIER();
   }
 
+  uint4 pre1[4][1];
+  const bf16* wp1[1];
   // ---- MLP layer 1 of both heads: [n, H] x [2*d0, H]^T, operand = LayerNorm of the last LSTM layer's h
   {
     for (int i = warp; i < my_rows; i += HF_WARPS) {
@@ -398,7 +437,8 @@ head_fused_kernel(const HeadFusedParams p) {
     }
     HF_ZERO_TAIL(H);
     hf_cluster_sync();
-    for (int it = cta; it < n1; it += G) {
+    if (cta < n1) {
+      const int it = cta;
       float acc[2][2][4];
 #pragma unroll
       for (int a = 0; a < 2; ++a)
@@ -406,10 +446,7 @@ head_fused_kernel(const HeadFusedParams p) {
         for (int b = 0; b < 2; ++b)
 #pragma unroll
           for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.0f;
-      const bf16* wp[2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) wp[q] = p.w_mlp1 + static_cast<size_t>(it * 16 + q * 8 + g) * H + t * 8;
-      hf_skinny_gemm<2>(A_s + static_cast<size_t>(g) * lda + t * 8, lda, two_m, wp, H, warp, acc);
+      hf_skinny_gemm<2>(A_s + static_cast<size_t>(g) * lda + t * 8, lda, two_m, wp2, H, warp, pre2, acc);
       __syncthreads();
       hf_store_partials<2>(red, mr, two_m, warp, lane, acc);
       __syncthreads();
@@ -417,6 +454,11 @@ head_fused_kernel(const HeadFusedParams p) {
         const int r = idx >> 4, cc = idx & 15, col = it * 16 + cc;
         p.mlp1[static_cast<size_t>(r) * 2 * d0 + col] = hf_reduce(red, mr, 16, r, cc) + __ldg(p.b_mlp1 + col);
       }
+    }
+    {
+      const int it = cta < n2 ? cta : 0;
+      wp1[0] = ((it / (d1 / 8)) ? p.w_mlp2_grip : p.w_mlp2_pose) + static_cast<size_t>((it % (d1 / 8)) * 8 + g) * d0 + t * 8;
+      if (cta < n2) hf_load_batch<1>(pre1, wp1, warp, d0 >> 5);
     }
     HF_BARRIER();
   }
@@ -431,16 +473,15 @@ head_fused_kernel(const HeadFusedParams p) {
     }
     HF_ZERO_TAIL(2 * d0);
     hf_cluster_sync();
-    for (int it = cta; it < n2; it += G) {
+    if (cta < n2) {
+      const int it = cta;
       const int head = it / (d1 / 8), c0 = (it % (d1 / 8)) * 8;
       float acc[2][1][4];
 #pragma unroll
       for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[a][0][c] = 0.0f;
-      const bf16* wp[1];
-      wp[0] = (head ? p.w_mlp2_grip : p.w_mlp2_pose) + static_cast<size_t>(c0 + g) * d0 + t * 8;
-      hf_skinny_gemm<1>(A_s + static_cast<size_t>(g) * lda + head * d0 + t * 8, lda, two_m, wp, d0, warp, acc);
+      hf_skinny_gemm<1>(A_s + static_cast<size_t>(g) * lda + head * d0 + t * 8, lda, two_m, wp1, d0, warp, pre1, acc);
       __syncthreads();
       hf_store_partials<1>(red, mr, two_m, warp, lane, acc);
       __syncthreads();
