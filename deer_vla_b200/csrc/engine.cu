@@ -237,18 +237,12 @@ static int run_attention(int impl, int dtype, const AttnParams& p, std::string* 
     const CUtensorMap* tv = attn_tmap(p.V, (uint64_t)p.B_host * p.Sk, width, p.ldv, AttnTc::HALF_ROWS);
     if (tq && tk && tv) {
       static bool attr_done = false;
-      // schedule A/B switches: v5 (two independent softmax groups, one thread per row) is the product path
-      static const int ver = getenv("DEER_ATTN_V3") ? 3 : (getenv("DEER_ATTN_V4") ? 4 : 5);
       if (!attr_done) {
-        cudaFuncSetAttribute(attn_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTc::SMEM_BYTES);
-        cudaFuncSetAttribute(attn_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTc::SMEM_BYTES);
         cudaFuncSetAttribute(attn_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTc5::SMEM_BYTES);
         attr_done = true;
       }
       const int grid = std::min(p.B_host * p.H, DEER_NUM_SMS);
-      auto kern = (ver == 3) ? attn_tc_kernel<3> : (ver == 4 ? attn_tc_kernel<4> : attn_tc5_kernel);
-      const size_t smem_bytes = (ver == 5) ? AttnTc5::SMEM_BYTES : AttnTc::SMEM_BYTES;
-      launch_k(kern, dim3(grid), dim3(AttnTc::THREADS), smem_bytes, st, pdl, *tq, *tk, *tv, reinterpret_cast<const bf16*>(p.Q), p.ldq,
+      launch_k(attn_tc5_kernel, dim3(grid), dim3(AttnTc5::THREADS), AttnTc5::SMEM_BYTES, st, pdl, *tq, *tk, *tv, reinterpret_cast<const bf16*>(p.Q), p.ldq,
                reinterpret_cast<bf16*>(p.O), p.ldo, p.B_host, p.H, p.Sq, p.Sk, p.scale * 1.4426950408889634f, g_attn_dbg);
       done = true;
     }
