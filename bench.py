@@ -332,8 +332,9 @@ def engine_arm(a):
     # ---- end-to-end through the public API with host buffers ------------------------------------
     h_frames = [(r.cpu().pin_memory(), g.cpu().pin_memory()) for r, g in frames[:2]]
     h_ids, h_mask, h_slots = ids.cpu().pin_memory(), mask.cpu().pin_memory(), slots.cpu().pin_memory()
+    # (same episode timesteps as the device-timed region: lead-in + warm-up steps after the reset, untimed, through the same path)
     eng.reset()
-    for t in range(2):
+    for t in range(lead_in + a.warmup):
         eng.step(h_frames[t % 2][0], h_frames[t % 2][1], h_ids, h_mask, h_slots, want_delta=False)
     barrier()
     t0 = time.perf_counter()
@@ -355,7 +356,7 @@ def engine_arm(a):
     u_frames = [(torch.randint(0, 256, (B, 200, 200, 3), dtype=torch.uint8, generator=gen).pin_memory(),
                  torch.randint(0, 256, (B, 84, 84, 3), dtype=torch.uint8, generator=gen).pin_memory()) for _ in range(2)]
     eng.reset()
-    for t in range(2):
+    for t in range(lead_in + a.warmup):
         eng.step_u8(u_frames[t % 2][0], u_frames[t % 2][1], h_ids, h_mask, h_slots)
     barrier()
     t0 = time.perf_counter()

@@ -655,8 +655,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
       // The fp32 residual of the NEXT tile is pulled into L2 now -- one tile period (a whole main loop) ahead of its use, while
       // this thread would otherwise wait for the accumulator: the epilogue's residual loads then cost an L2 hit instead of an
-      // HBM round trip (it was latency-bound on them: vit.out+res long_scoreboard 29 %, tensor pipe 54 %).
-      if (epi.resid != nullptr && epi.dbg != 4 && tile + num_clusters < num_tiles) {
+      // HBM round trip (it was latency-bound on them: vit.out+res long_scoreboard 29 %, tensor pipe 48 -> 56 %).  Only for K <= 1024:
+      // with a longer main loop the epilogue has slack anyway and the prefetched lines are evicted before they are used (ncu:
+      // vit.fc2+res, K = 4096, read 2.0 GB instead of 1.5 GB per launch with the prefetch on).
+      if (epi.resid != nullptr && epi.dbg != 4 && num_kb <= 16 && tile + num_clusters < num_tiles) {
         const int nt = tile + num_clusters;
         const int prow = (nt / n_blocks) * G::BM + static_cast<int>(rank) * 128 + lane_grp * 32 + lane;
         const int pcol = (nt % n_blocks) * G::BN;

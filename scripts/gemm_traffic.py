@@ -1,6 +1,8 @@
-"""profiles/r01_gemm_traffic.json from the per-launch ncu metrics of ONE step (scripts/one_step.py under ncu, see its docstring):
-DRAM bytes per GEMM launch (what bench.py reports as roofline.traffic) and the time-weighted tensor-pipe activity.
-  python scripts/gemm_traffic.py gpurun_out/step_metrics.csv > profiles/r01_gemm_traffic.json"""
+"""profiles/r02_gemm_traffic.json from the per-launch ncu metrics of the TIMED steps of the bench command itself
+(DEER_NCU_RANGE=1 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,
+sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed ... python bench.py --steps 1 --warmup 3, scripts/gpu_r2f.sh):
+DRAM bytes per GEMM launch (bench.py reports it as roofline.traffic, labelled static) and the time-weighted tensor-pipe activity.
+  python scripts/gemm_traffic.py gpurun_out/r2f_step_metrics.csv deer_b 224 "<when / commit>" > profiles/r02_gemm_traffic.json"""
 import collections, csv, json, re, sys
 rows = collections.OrderedDict()
 for r in csv.DictReader(l for l in open(sys.argv[1]) if not l.startswith("==")):
@@ -17,9 +19,11 @@ g = [d for d in rows.values() if d["name"].startswith("gemm_tc")]
 t = sum(d["us"] for d in g)
 big = [d for d in g if d["us"] > 150]
 print(json.dumps({
-    "source": "ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,"
-              "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none python scripts/one_step.py "
-              "(one DeeR-B step, B=224; every gemm_tc2_kernel / gemm_tc_kernel launch)",
+    "source": "DEER_NCU_RANGE=1 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,"
+              "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none python bench.py --steps 1 --warmup 3 "
+              "(the timed step of the bench command; every gemm_tc2_kernel / gemm_tc_kernel launch)",
+    "workload": sys.argv[2] if len(sys.argv) > 2 else "deer_b", "episodes_per_gpu": int(sys.argv[3]) if len(sys.argv) > 3 else 224,
+    "captured_at": sys.argv[4] if len(sys.argv) > 4 else "",
     "launches": len(g),
     "dram_read_bytes_per_launch": sum(d.get("dram__bytes_read.sum", 0) for d in g) / len(g),
     "dram_write_bytes_per_launch": sum(d.get("dram__bytes_write.sum", 0) for d in g) / len(g),
