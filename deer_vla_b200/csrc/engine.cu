@@ -1041,10 +1041,15 @@ template <typename T> struct StepImpl {
   int vision(const float* rgb, const float* grip) {
     const deer_config& f = c->cfg;
     const int NI = 2 * n, np = c->np, L = c->L, Wd = f.vit_width, NImax = 2 * f.max_batch;
-    im2col_kernel<T><<<NI * np, 128, 0, st>>>(rgb, grip, tp(c->im_cols), n, f.image_size, f.patch, c->Kp);
+    im2col_kernel<T><<<DEER_NUM_SMS * 8, 256, 0, st>>>(rgb, grip, tp(c->im_cols), n, f.image_size, f.patch, c->Kp);
     KLAUNCH_CHECK("im2col");
     RET(gemm(c->im_cols, c->Kp, NImax * np, c->w_conv, c->Kp, NI * np, Wd, c->Kp, c->patch_out, Wd, 0, nullptr, ACT_NONE, nullptr, nullptr, 0, nullptr, 0));
-    vit_assemble_kernel<T><<<NI * L, 128, 0, st>>>(tp(c->patch_out), c->v_cls, c->v_pos, c->v_lnpre_g, c->v_lnpre_b, c->vx, NI, L, Wd);
+    if (Wd == 1024)
+      vit_assemble_warp_kernel<T, 8><<<(NI * L + 3) / 4, 128, 0, st>>>(tp(c->patch_out), c->v_cls, c->v_pos, c->v_lnpre_g, c->v_lnpre_b, c->vx, NI, L);
+    else if (Wd == 128)
+      vit_assemble_warp_kernel<T, 1><<<(NI * L + 3) / 4, 128, 0, st>>>(tp(c->patch_out), c->v_cls, c->v_pos, c->v_lnpre_g, c->v_lnpre_b, c->vx, NI, L);
+    else
+      vit_assemble_kernel<T><<<NI * L, 128, 0, st>>>(tp(c->patch_out), c->v_cls, c->v_pos, c->v_lnpre_g, c->v_lnpre_b, c->vx, NI, L, Wd);
     KLAUNCH_CHECK("vit_assemble");
     const int Mmax = NImax * L;
     const LnMap id{0, 0, 0};

@@ -26,21 +26,27 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // padded to Kp.  Image order: all rgb frames, then all gripper frames.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void im2col_kernel(const float* __restrict__ rgb, const float* __restrict__ grip, T* __restrict__ out,
-                              int n, int H, int P, int Kp) {
-  const int g = H / P, np = g * g;
-  const int row = blockIdx.x;                 // 0 .. 2n*np
-  const int img = row / np, p = row % np;
-  const float* src = (img < n ? rgb + static_cast<size_t>(img) * 3 * H * H : grip + static_cast<size_t>(img - n) * 3 * H * H);
-  const int py = p / g, px = p % g;
-  const int K = 3 * P * P;
-  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
-    float v = 0.0f;
-    if (k < K) {
-      const int c = k / (P * P), rem = k % (P * P), ky = rem / P, kx = rem % P;
-      v = src[(static_cast<size_t>(c) * H + (py * P + ky)) * H + (px * P + kx)];
+__global__ void __launch_bounds__(256)
+im2col_kernel(const float* __restrict__ rgb, const float* __restrict__ grip, T* __restrict__ out,
+              int n, int H, int P, int Kp) {
+  // one thread per (operand row, channel, patch line): P contiguous floats of the frame -> P contiguous operand elements, so the
+  // index arithmetic (six integer divisions) is paid once per P elements; one extra thread per row zeroes the K..Kp padding
+  const int g = H / P, np = g * g, K = 3 * P * P, per_row = 3 * P + 1;
+  const long long total = static_cast<long long>(2 * n) * np * per_row;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int u = static_cast<int>(i % per_row);
+    const long long row = i / per_row;
+    T* orow = out + row * Kp;
+    if (u == 3 * P) {
+      for (int k = K; k < Kp; ++k) orow[k] = from_f32<T>(0.0f);
+      continue;
     }
-    out[static_cast<size_t>(row) * Kp + k] = from_f32<T>(v);
+    const int img = static_cast<int>(row / np), p = static_cast<int>(row % np);
+    const int c = u / P, ky = u % P, py = p / g, px = p % g;
+    const float* src = (img < n ? rgb + static_cast<size_t>(img) * 3 * H * H : grip + static_cast<size_t>(img - n) * 3 * H * H) +
+                       (static_cast<size_t>(c) * H + (py * P + ky)) * H + px * P;
+    T* dst = orow + c * P * P + ky * P;
+    for (int kx = 0; kx < P; ++kx) dst[kx] = from_f32<T>(__ldg(src + kx));
   }
 }
 
@@ -165,6 +171,47 @@ layernorm_warp_kernel(const TIn* in, int in_ld, LnMap in_map, const float* __res
 }
 
 // ViT token assembly + ln_pre: x[img, 0] = cls + pos[0]; x[img, 1+p] = patch[img*np+p] + pos[1+p]; x = ln_pre(x)
+// One WARP per token row (4 rows per CTA), the row held in registers as float4s (D = NVEC * 128), two-pass fp32 statistics.
+template <typename T, int NVEC>
+__global__ void __launch_bounds__(128)
+vit_assemble_warp_kernel(const T* __restrict__ patch, const float* __restrict__ cls, const float* __restrict__ pos,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ x, int n_img, int L) {
+  constexpr int D = NVEC * 128;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= n_img * L) return;
+  const int img = r / L, tok = r % L;
+  float4 v[NVEC];
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    const int j = (lane + 32 * i) * 4;
+    float4 t = (tok == 0) ? *reinterpret_cast<const float4*>(cls + j)
+                          : Vec4IO<T>::ld(patch + (static_cast<size_t>(img) * (L - 1) + (tok - 1)) * D + j);
+    const float4 pe = *reinterpret_cast<const float4*>(pos + static_cast<size_t>(tok) * D + j);
+    t.x += pe.x; t.y += pe.y; t.z += pe.z; t.w += pe.w;
+    v[i] = t;
+    s += (t.x + t.y) + (t.z + t.w);
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    const int j = (lane + 32 * i) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + j), b = *reinterpret_cast<const float4*>(beta + j);
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + b.x; y.y = (v[i].y - mean) * rstd * g.y + b.y;
+    y.z = (v[i].z - mean) * rstd * g.z + b.z; y.w = (v[i].w - mean) * rstd * g.w + b.w;
+    *reinterpret_cast<float4*>(x + static_cast<size_t>(r) * D + j) = y;
+  }
+}
+// general widths: one CTA per token row
 template <typename T>
 __global__ void __launch_bounds__(128)
 vit_assemble_kernel(const T* __restrict__ patch, const float* __restrict__ cls, const float* __restrict__ pos,
