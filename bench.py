@@ -209,7 +209,7 @@ def reference_arm(a):
     fam, max_layer, exit_ratio, desc = workload(a)
     r = run_cpu_reference(workload(a), a.steps, a.warmup, a.seq)
     line = {"impl": "reference", "metric": "action-steps/sec (device-timed)", "value": r["value"], "unit": "action-steps/s", "n_gpus": a.gpus,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak" if a.weak else "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "batch_per_step": 1, "seq_len": a.seq, "max_layer": max_layer, "exit_ratio": exit_ratio,
                        "note": "reference CPU path = oracle port of the PyTorch eager forward (the reference is Python; "

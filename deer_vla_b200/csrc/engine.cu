@@ -1041,7 +1041,8 @@ template <typename T> struct StepImpl {
   int vision(const float* rgb, const float* grip) {
     const deer_config& f = c->cfg;
     const int NI = 2 * n, np = c->np, L = c->L, Wd = f.vit_width, NImax = 2 * f.max_batch;
-    im2col_kernel<T><<<DEER_NUM_SMS * 8, 256, 0, st>>>(rgb, grip, tp(c->im_cols), n, f.image_size, f.patch, c->Kp);
+    if (f.patch == 14) im2col_kernel<T, 14><<<NI * np, 128, 0, st>>>(rgb, grip, tp(c->im_cols), n, f.image_size, f.patch, c->Kp);
+    else im2col_kernel<T, 0><<<NI * np, 128, 0, st>>>(rgb, grip, tp(c->im_cols), n, f.image_size, f.patch, c->Kp);
     KLAUNCH_CHECK("im2col");
     RET(gemm(c->im_cols, c->Kp, NImax * np, c->w_conv, c->Kp, NI * np, Wd, c->Kp, c->patch_out, Wd, 0, nullptr, ACT_NONE, nullptr, nullptr, 0, nullptr, 0));
     if (Wd == 1024)

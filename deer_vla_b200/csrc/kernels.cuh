@@ -25,28 +25,31 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // out[(img*np + p), k] with k = c*P*P + ky*P + kx  (== conv weight [out,c,ky,kx] flattened), zero
 // padded to Kp.  Image order: all rgb frames, then all gripper frames.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+// PC > 0: patch size known at compile time (14 for ViT-L/14: every division below becomes a multiply-shift); PC = 0: runtime P.
+template <typename T, int PC>
 __global__ void __launch_bounds__(256)
 im2col_kernel(const float* __restrict__ rgb, const float* __restrict__ grip, T* __restrict__ out,
-              int n, int H, int P, int Kp) {
-  // one thread per (operand row, channel, patch line): P contiguous floats of the frame -> P contiguous operand elements, so the
-  // index arithmetic (six integer divisions) is paid once per P elements; one extra thread per row zeroes the K..Kp padding
-  const int g = H / P, np = g * g, K = 3 * P * P, per_row = 3 * P + 1;
-  const long long total = static_cast<long long>(2 * n) * np * per_row;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int u = static_cast<int>(i % per_row);
-    const long long row = i / per_row;
-    T* orow = out + row * Kp;
-    if (u == 3 * P) {
-      for (int k = K; k < Kp; ++k) orow[k] = from_f32<T>(0.0f);
-      continue;
+              int n, int H, int P_rt, int Kp) {
+  const int P = PC > 0 ? PC : P_rt;
+  const int g = H / P, np = g * g;
+  const int K = 3 * P * P;
+  // 256 threads walk k (fastest) of two operand rows per CTA pass: consecutive threads read consecutive pixels of a patch line
+  // and write consecutive operand elements
+  const int rows = 2 * n * np;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int img = row / np, p = row % np;
+    const float* src = (img < n ? rgb + static_cast<size_t>(img) * 3 * H * H : grip + static_cast<size_t>(img - n) * 3 * H * H);
+    const int py = p / g, px = p % g;
+    const float* base = src + static_cast<size_t>(py * P) * H + px * P;
+    T* orow = out + static_cast<size_t>(row) * Kp;
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+      float v = 0.0f;
+      if (k < K) {
+        const int c = k / (P * P), rem = k - c * (P * P), ky = rem / P, kx = rem - ky * P;
+        v = __ldg(base + (static_cast<size_t>(c) * H + ky) * H + kx);
+      }
+      orow[k] = from_f32<T>(v);
     }
-    const int img = static_cast<int>(row / np), p = static_cast<int>(row % np);
-    const int c = u / P, ky = u % P, py = p / g, px = p % g;
-    const float* src = (img < n ? rgb + static_cast<size_t>(img) * 3 * H * H : grip + static_cast<size_t>(img - n) * 3 * H * H) +
-                       (static_cast<size_t>(c) * H + (py * P + ky)) * H + px * P;
-    T* dst = orow + c * P * P + ky * P;
-    for (int kx = 0; kx < P; ++kx) dst[kx] = from_f32<T>(__ldg(src + kx));
   }
 }
 
