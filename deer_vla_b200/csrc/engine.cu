@@ -62,6 +62,19 @@ static bool make_tmap(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t 
   return r == CUDA_SUCCESS;
 }
 
+// bf16 row-major output [rows, cols] with row pitch ld: box = 32 columns x 32 rows, 64-byte swizzle (the TMA-store epilogue's tile)
+static bool make_tmap_c(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 // Launch with (optionally) programmatic stream serialization: the kernel may begin while its predecessor drains; the kernels
 // launched this way all start with pdl_wait() (common.cuh).  DEER_PDL=0 turns it off (A/B), and it is never used during graph capture.
 static bool g_launch_overlap = getenv("DEER_PDL") ? atoi(getenv("DEER_PDL")) != 0 : true;
@@ -121,8 +134,8 @@ static cudaError_t launch_tc(GemmCtx& g, const CUtensorMap& ta, const CUtensorMa
   return launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(G::THREADS), G::SMEM_BYTES, st, g.pdl, ta, tb, M, m_dev, m_mul, N, K, epi);
 }
 
-static cudaError_t launch_tc2(GemmCtx& g, const CUtensorMap& ta, const CUtensorMap& tb, int M, const int* m_dev, int m_mul, int N, int K,
-                              const GemmEpi& epi, cudaStream_t st) {
+static cudaError_t launch_tc2(GemmCtx& g, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, const int* m_dev, int m_mul,
+                              int N, int K, const GemmEpi& epi, cudaStream_t st) {
   using G = GemmTc2;
   if (!g.attr_set[3]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
@@ -131,7 +144,7 @@ static cudaError_t launch_tc2(GemmCtx& g, const CUtensorMap& ta, const CUtensorM
   }
   const int tiles = ((M + 255) / 256) * ((N + 255) / 256);
   const int clusters = std::max(1, std::min(tiles, DEER_NUM_SMS / 2));
-  return launch_k(gemm_tc2_kernel, dim3(2 * clusters), dim3(G::THREADS), G::SMEM_BYTES, st, g.pdl, ta, tb, M, m_dev, m_mul, N, K, epi);
+  return launch_k(gemm_tc2_kernel, dim3(2 * clusters), dim3(G::THREADS), G::SMEM_BYTES, st, g.pdl, ta, tb, tc, M, m_dev, m_mul, N, K, epi);
 }
 
 // dtype: 0 bf16, 1 fp32.  impl: DEER_GEMM_* (2 = force the 1-CTA tcgen05 kernel, for A/B comparisons).  a_rows: allocated rows of A (>= M) for the TMA bounds.
@@ -194,7 +207,26 @@ static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int
       if (!make_tmap(&tm, W, N, K, ldw, BN)) return set_err(g.err, DEER_E_CUDA, "cuTensorMapEncodeTiled failed for W (%d x %d ld %d)", N, K, ldw);
       ib = g.tmaps.emplace(kb, tm).first;
     }
-    if (use2) e = launch_tc2(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st);
+    if (use2) {
+      // bf16 output without a residual leaves through shared memory + TMA stores (DEER_GEMM_TMA_STORE=0: the transposing epilogue, A/B)
+      const char* ts_env = getenv("DEER_GEMM_TMA_STORE");                // read per call: tests flip it inside one process
+      const bool tma_store_on = ts_env ? atoi(ts_env) != 0 : true;
+      GemmEpi e2 = epi;
+      const CUtensorMap* tc = &ia->second;
+      if (tma_store_on && !epi.out_f32 && epi.resid == nullptr && (N % 32) == 0 && (epi.ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(epi.C) & 15) == 0 &&
+          (epi.bias == nullptr || (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0)) {
+        TmapKey kc{epi.C, (uint64_t)M, (uint64_t)N, (uint64_t)epi.ldc, 3232u};       // rows = M: the hardware clips the last tile's rows
+        auto ic = g.tmaps.find(kc);
+        if (ic == g.tmaps.end()) {
+          CUtensorMap tm;
+          if (!make_tmap_c(&tm, epi.C, M, N, epi.ldc)) return set_err(g.err, DEER_E_CUDA, "cuTensorMapEncodeTiled failed for C (%d x %d ld %d)", M, N, epi.ldc);
+          ic = g.tmaps.emplace(kc, tm).first;
+        }
+        tc = &ic->second;
+        e2.tma_store = 1;
+      }
+      e = launch_tc2(g, ia->second, ib->second, *tc, M, m_dev, m_mul, N, K, e2, st);
+    }
     else if (BN == 256) e = launch_tc<256>(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st, 0);
     else if (BN == 128) e = launch_tc<128>(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st, 1);
     else e = launch_tc<64>(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st, 2);

@@ -22,6 +22,7 @@ struct GemmEpi {
   int ldr;
   int dbg;             // 0 normal; tuning only: 2 = skip the epilogue's math and stores in the 2-CTA kernel (mainloop-only timing),
                        // 4 = no L2 prefetch of the next tile's residual (A/B)
+  int tma_store;       // 2-CTA kernel, bf16 output without residual: rows leave through shared memory + cp.async.bulk.tensor stores (tmC)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -88,6 +89,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// shared -> global tile store (bulk async-group completion); coordinates (c0 = column, c1 = row); rows / columns outside the tensor
+// map are clipped by the hardware
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tm), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
@@ -535,6 +546,43 @@ __device__ __forceinline__ void epi_store_coalesced(const GemmEpi& e, float sc, 
   else epi_store_coalesced_t<ACT_RELU, false>(e, sc, row0, col0, M, N, v, stage, lane);
 }
 
+// bf16 output without residual, through shared memory and a TMA store: the thread that owns accumulator row r (TMEM lane) applies
+// bias / activation / scale to its 32 columns, packs them to 64 bytes and writes them as the row of a [32 rows][64 B] tile in the
+// 64-byte-swizzle layout the tensor map expects (16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3): the eight lanes of a
+// store phase hit eight different bank groups), then ONE cp.async.bulk.tensor instruction per warp moves the tile.  Against the
+// transposing epilogue this drops the fp32 staging round trip through shared memory (4.6 KB written + read per chunk -> 2 KB
+// written) and all per-thread global stores.  `buf`: this warp's 2 KB buffer (512-byte aligned).
+template <int ACT>
+__device__ __forceinline__ void epi_tma_store_t(const GemmEpi& e, const CUtensorMap* tmC, float sc, int row0, int col0, float (&v)[32],
+                                                uint8_t* buf, int lane) {
+  uint32_t w[16];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + j));
+    const float4 t = epi_math4<ACT>(make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]), b4, sc);
+    w[j >> 1] = pack_bf16x2(t.x, t.y);
+    w[(j >> 1) + 1] = pack_bf16x2(t.z, t.w);
+  }
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(buf + lane * 64 + ((c ^ sw) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tmC, buf, col0, row0);
+    tma_store_commit();
+  }
+}
+__device__ __forceinline__ void epi_tma_store(const GemmEpi& e, const CUtensorMap* tmC, float sc, int row0, int col0, float (&v)[32],
+                                              uint8_t* buf, int lane) {
+  if (e.act == ACT_NONE) epi_tma_store_t<ACT_NONE>(e, tmC, sc, row0, col0, v, buf, lane);
+  else if (e.act == ACT_GELU) epi_tma_store_t<ACT_GELU>(e, tmC, sc, row0, col0, v, buf, lane);
+  else if (e.act == ACT_QUICKGELU) epi_tma_store_t<ACT_QUICKGELU>(e, tmC, sc, row0, col0, v, buf, lane);
+  else epi_tma_store_t<ACT_RELU>(e, tmC, sc, row0, col0, v, buf, lane);
+}
+
 struct GemmTc2 {
   static constexpr int BM = 256, BN = 256, BK = 64, UMMA_K = 16;
   static constexpr int A_BYTES = 128 * BK * 2;        // this CTA's 128 rows of A
@@ -550,7 +598,7 @@ struct GemmTc2 {
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmTc2::THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                 int M_host, const int* __restrict__ m_dev, int m_mul, int N, int K, GemmEpi epi) {
   using G = GemmTc2;
   extern __shared__ uint8_t smem_raw[];
@@ -572,6 +620,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (epi.tma_store) tma_prefetch_desc(&tmC);
     for (int s = 0; s < G::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);                      // only the leader's is used: its own arrive.expect_tx
       mbar_init(&empty_bar[s], 1);                     // one multicast tcgen05.commit per phase
@@ -648,6 +697,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int col_part = ew >> 2;                       // 0..2: the eight 32-column chunks are split 3 / 3 / 2
     const int c_begin = col_part * 3, c_end = (col_part == 2) ? 8 : c_begin + 3;
     float* stage = epi_stage + ew * (32 * 36);
+    uint8_t* obuf = reinterpret_cast<uint8_t*>(stage);   // TMA-store path: two 2 KB tiles inside this warp's 4.5 KB staging region
+    int ob = 0;
     const float sc = (epi.scale != nullptr) ? __ldg(epi.scale) : 1.0f;
     int as = 0;
     uint32_t aph = 0;
@@ -677,7 +728,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
         tmem_ld_wait();
         const int col0 = n_blk * G::BN + c * 32;
-        if (epi.dbg != 2 && row0 < M && col0 < N) epi_store_coalesced(epi, sc, row0, col0, M, N, v, stage, lane);
+        if (epi.dbg != 2 && row0 < M && col0 < N) {
+          if (epi.tma_store) {
+            if (lane == 0) tma_store_wait_read<1>();       // the store issued two chunks ago (same buffer) has read its tile
+            __syncwarp();
+            epi_tma_store(epi, &tmC, sc, row0, col0, v, obuf + ob * 2048, lane);
+            ob ^= 1;
+          } else {
+            epi_store_coalesced(epi, sc, row0, col0, M, N, v, stage, lane);
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -685,6 +745,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
   }
+  if (epi.tma_store && warp >= 2 && lane == 0) tma_store_wait_all();     // this thread's bulk stores have been written
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) {

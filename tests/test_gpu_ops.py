@@ -246,3 +246,30 @@ def test_llm_attention_mma_vs_simt_and_torch(case):
         err = (outs[impl][: B - 1] - ref[: B - 1]).abs().max().item()
         assert err <= 2e-2, (impl, err)                                                    # bf16 output rounding of O(1) values
     assert (outs["mma"] - outs["simt"]).abs().max().item() <= 2e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(5003, 3072, 1024), (9000, 512, 2048), (14392, 4096, 512)])
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_gemm_tma_store_epilogue_is_bit_identical(M, N, K, act):
+    """2-CTA kernel, bf16 output without residual: the TMA-store epilogue (row-per-lane, 64-byte-swizzled tile, one
+    cp.async.bulk.tensor per warp) against the transposing per-thread-store epilogue (DEER_GEMM_TMA_STORE=0) on the same inputs:
+    BIT-identical (same bias / activation / scale / rounding), the ragged last row tile (M % 32 != 0) clipped by the tensor map,
+    with and without bias."""
+    import os
+    from deer_vla_b200.engine import op_gemm
+    g = torch.Generator(device="cuda").manual_seed(M + act)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    outs = {}
+    for flag in ("1", "0"):
+        os.environ["DEER_GEMM_TMA_STORE"] = flag
+        try:
+            outs[flag] = (op_gemm(A, W, bias=bias, act=act, impl="tcgen05").clone(), op_gemm(A, W, act=act, impl="tcgen05").clone())
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("DEER_GEMM_TMA_STORE", None)
+    for a, b in zip(outs["1"], outs["0"]):
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+    ref = _ref_gemm(A, W, bias, act, None, None)
+    assert (outs["1"][0].float() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
