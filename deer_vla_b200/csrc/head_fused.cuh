@@ -76,7 +76,7 @@ __device__ __forceinline__ void hf_grid_barrier(unsigned long long* bar, unsigne
     const long long t0 = clock64();
     while (ld_acquire_u64(bar) < target) {
       __nanosleep(32);
-      if (clock64() - t0 > 6000000000LL) __trap();
+      if (clock64() - t0 > 40000000000LL) __trap();     // ~20 s: far beyond any real wait, also under compute-sanitizer's slow-down
     }
     __threadfence();
   }
@@ -279,6 +279,7 @@ head_fused_kernel(const HeadFusedParams p) {
   const int n1 = 2 * d0 / 16;                              // MLP1 items: 16 columns
   const int n2 = 2 * d1 / 8;                               // MLP2 items: 8 columns
   if (threadIdx.x < 32) s_slot[threadIdx.x] = (threadIdx.x < n) ? p.slot[threadIdx.x] : 0;
+  hf_cluster_sync();                                       // every CTA of the cluster is running before anyone addresses a peer's shared memory
 
   HF_MARK(0);
   // ---- L2 prefetch of every weight row this CTA will stream, in phase order (82 MB over the grid; L2 holds 126 MB)
