@@ -448,8 +448,9 @@ def test_head_path_switch_at_32_episodes_is_consistent():
             outs.append({k: v.cpu().numpy().copy() for k, v in o.items()})
         res[n] = outs
         eng.close()
+    alive = np.ones(32, dtype=bool)                                   # episodes whose exits agreed so far (same carried state)
     for t in range(T):
         a, b = res[33][t], res[32][t]
-        same = a["exit_layer"][:32] == b["exit_layer"]
-        assert same.mean() >= 0.9, (t, same.mean())                  # a rounding-level flip may happen on a near-threshold episode
-        assert np.abs(a["pose"][:32][same] - b["pose"][same]).max() <= (8e-3 if t == 0 else 3e-2)
+        alive &= a["exit_layer"][:32] == b["exit_layer"]              # a rounding-level flip may happen on a near-threshold episode
+        assert alive.mean() >= 0.75, (t, alive.mean())
+        assert np.abs(a["pose"][:32][alive] - b["pose"][alive]).max() <= (8e-3 if t == 0 else 3e-2)
