@@ -270,7 +270,9 @@ def engine_arm(a):
     WIN = 12
     gen = torch.Generator().manual_seed(4242 + rank)
     cols = []
-    for w in range(a.calib_windows):
+    # at least ~400 delta samples per exit over the whole job (6 per episode and window): small shards calibrate on more windows
+    n_windows = max(a.calib_windows, -(-400 // (6 * B * world)))
+    for w in range(n_windows):
         order = [(w * 5 + t) % NF for t in range(WIN)]
         win = {"rgb": torch.stack([frames[i][0] for i in order], dim=1), "gripper": torch.stack([frames[i][1] for i in order], dim=1), "ids": ids}
         cols.append(generate_action_values_window(eng, [win], window_size=WIN, generator=gen))
