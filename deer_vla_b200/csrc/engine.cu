@@ -908,7 +908,13 @@ extern "C" int deer_finalize_weights(deer_ctx* c) {
     const std::string p(b);
     if (f.qk_ln) {
       RET(pack_f32(c, p + "ln_1.weight", {D}, &w.ln1_g)); RET(pack_f32(c, p + "ln_2.weight", {D}, &w.ln2_g));
-      RET(pack_f32(c, p + "attn.q_ln.weight", {D}, &w.qln_g)); RET(pack_f32(c, p + "attn.k_ln.weight", {D}, &w.kln_g));
+      {                                                    // [q_ln | k_ln] weights back to back: one LayerNorm launch covers both
+        std::vector<float> gq, gk;
+        RET(host_vec(c, p + "attn.q_ln.weight", {D}, &gq)); RET(host_vec(c, p + "attn.k_ln.weight", {D}, &gk));
+        gq.insert(gq.end(), gk.begin(), gk.end());
+        RET(upload_f32(c, gq, &w.qln_g));
+        w.kln_g = w.qln_g + D;
+      }
       RET(pack_mat(c, p + "mlp.mlp_up.weight", f.mlp_ratio * D, D, &w.w_up));
       RET(pack_mat(c, p + "mlp.mlp_down.weight", D, f.mlp_ratio * D, &w.w_down));
     } else {
@@ -1171,8 +1177,10 @@ template <typename T> struct StepImpl {
     RET(ln<float, T>(x, D, w.ln1_g, nullptr, 1, D, tp(c->l_ln), D, id, nullptr, 0, 0, M, nd, S));
     RET(gemm(c->l_ln, D, Mmax, w.w_qkv, D, M, 3 * D, D, c->l_qkv, 3 * D, 0, nullptr, ACT_NONE, nullptr, nullptr, 0, nd, S));
     if (f.qk_ln) {   // LayerNorm over the full d_model of q and of k before the head split (attn_qk_ln)
-      RET(ln<T, T>(tp(c->l_qkv), 3 * D, w.qln_g, nullptr, 1, D, tp(c->l_qkv), 3 * D, id, nullptr, 0, 0, M, nd, S));
-      RET(ln<T, T>(tp(c->l_qkv) + D, 3 * D, w.kln_g, nullptr, 1, D, tp(c->l_qkv) + D, 3 * D, id, nullptr, 0, 0, M, nd, S));
+      // ONE launch for both: logical row r = 2 * token + part (part 0 = q, 1 = k) lives at row 3 * token + part of the [.., D]-pitched
+      // view of the fused qkv buffer; gamma group r % 2
+      const LnMap qk{2, 3, 0};
+      RET(ln<T, T>(tp(c->l_qkv), D, w.qln_g, nullptr, 2, D, tp(c->l_qkv), D, qk, nullptr, 0, 0, 2 * M, nd, 2 * S, qk));
     }
     AttnParams a{};
     a.Q = c->l_qkv; a.K = tp(c->l_qkv) + D; a.V = tp(c->l_qkv) + 2 * D; a.O = c->l_att;
