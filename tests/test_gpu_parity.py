@@ -4,13 +4,13 @@ vectors generated from the unmodified reference (oracle/make_golden.py).
 Tolerances (stated per test):
   * fp32 validation path: every tap <= 2e-4 abs, exit indices identical (bit-exact decisions).
   * bf16 product path: the north-star tolerance is "1e-3 bf16"; a bf16 stack of 24 ViT + 12 LLM
-    layers cannot meet 1e-3 absolute on tanh outputs against an fp32 oracle, so the test states what
-    it measures: pose within 5e-2 abs of the fp32 oracle (measured worst case 3.0e-2 at 3B size, 1e-2
-    typical), and exit indices identical on every sample whose |delta - T| margin exceeds 0.02
-    (decisions inside the margin are rounding, not logic).  The size of "bf16 tolerance" itself is
+    layers cannot meet 1e-3 absolute on tanh outputs against an fp32 oracle, so "bf16 tolerance" is
     measured, not assumed: tests/golden/yardstick3b.npz holds the oracle run with bf16-rounded
-    contraction operands (Y = 1.4e-2..1.8e-2 on poses vs the fp32 oracle at 3B size), and the engine
-    must stay within 1.5*Y (+2e-3) of the fp32 oracle (test_full3b_bf16_within_rounding_yardstick).
+    contraction operands (Y = 1.2e-2..1.8e-2 on poses vs the fp32 oracle at 3B size), and the engine
+    must stay within 1.5*Y (+2e-3) of the fp32 oracle (test_full3b_bf16_within_rounding_yardstick;
+    2.5*Y at 9B size).  The multi-step 3B comparisons against the reference's golden rollouts (asserted
+    exact-match set, re-seeding after a rounding-level flip, fp32 path bit-exact on every decision) live
+    in tests/test_gpu_round2.py.
 """
 import os
 
@@ -371,7 +371,7 @@ def test_full9b_bf16_within_rounding_yardstick():
     every exit's delta and the final pose are compared and no threshold decision can flip.  Bar = the measured rounding
     yardstick of THIS model size (tests/golden/yardstick9b.npz, `python -m oracle.make_golden --yardstick-only --family 9b`):
     the oracle with bf16-rounded contraction operands differs from the fp32 oracle by Y (2.5e-2 .. 3.9e-2 on poses here, twice
-    the 3B figure -- the stack is twice as wide); the engine must be within 3*Y of both.  The MPT-7B block itself is cross-checked
+    the 3B figure -- the stack is twice as wide); the engine must be within 2.5*Y of both (measured <= 2.1*Y).  The MPT-7B block itself is cross-checked
     against transformers.models.mpt (tests/golden/xcheck.json); the reference's own modeling_gpt_9b.py cannot be driven here
     (13 un-vendored sibling modules), so this checks the engine against the restatement only."""
     ocfg = O.config_9b(12)
