@@ -231,7 +231,9 @@ int deer_get_stats(deer_ctx* ctx, deer_stats* out);
 /* single-operator entry points (DEVICE pointers) so that kernels can be parity-tested in isolation.
  * dtype: 0 = bf16, 1 = fp32 for A/W (and C unless out_f32).   C[M,N] = epi(A[M,K] @ W[N,K]^T).
  * epilogue: v = acc (+bias[n]); act 0 none / 1 GELU(erf) / 2 QuickGELU / 3 ReLU; v *= *scale (if scale);
- * v += resid[m,n] (fp32, ldc) (if resid).  m_dev (optional device int) clamps M to *m_dev * m_mul. */
+ * v += resid[m,n] (fp32, ldc) (if resid).  m_dev (optional device int) clamps M to *m_dev * m_mul; rows at or beyond that count are
+ * never written for fp32 / residual outputs, while a bf16 output without residual leaves through whole 32-row TMA tiles, so its rows
+ * between the device-side count and M are scratch (they may be overwritten; rows >= M never are). */
 int deer_op_gemm(int impl, int dtype, const void* A, int lda, const void* W, int ldw, void* C, int ldc,
                  int M, int N, int K, const float* bias, int act, const float* scale, const float* resid,
                  int out_f32, const int32_t* m_dev, int m_mul, void* stream);
