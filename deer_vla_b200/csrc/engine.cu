@@ -109,6 +109,26 @@ struct GemmCtx {
   LaunchStats* stats = nullptr;
   std::string* err = nullptr;
   bool pdl = false;            // programmatic dependent launch allowed (off while a CUDA graph is being captured)
+  // split-K workspace of the few-row launches (gemm_tc_splitk_kernel): fp32 partial tiles + one arrival counter per tile
+  float* sk_ws = nullptr;
+  int* sk_cnt = nullptr;
+  size_t sk_ws_bytes = 0;
+  bool sk_attr = false;
+  bool alloc_splitk() {
+    if (sk_ws) return true;
+    const size_t bytes = size_t(16) << 20;
+    if (cudaMalloc(&sk_ws, bytes) != cudaSuccess) { sk_ws = nullptr; return false; }
+    if (cudaMalloc(&sk_cnt, 256 * sizeof(int)) != cudaSuccess || cudaMemset(sk_cnt, 0, 256 * sizeof(int)) != cudaSuccess) {
+      cudaFree(sk_ws); sk_ws = nullptr; if (sk_cnt) cudaFree(sk_cnt); sk_cnt = nullptr; return false;
+    }
+    sk_ws_bytes = bytes;
+    return true;
+  }
+  void free_splitk() {
+    if (sk_ws) cudaFree(sk_ws);
+    if (sk_cnt) cudaFree(sk_cnt);
+    sk_ws = nullptr; sk_cnt = nullptr; sk_ws_bytes = 0;
+  }
   // profiling
   bool profile = false;
   int tag = 0, epoch = 0;
@@ -134,6 +154,18 @@ static cudaError_t launch_tc(GemmCtx& g, const CUtensorMap& ta, const CUtensorMa
   return launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(G::THREADS), G::SMEM_BYTES, st, g.pdl, ta, tb, M, m_dev, m_mul, N, K, epi);
 }
 
+static cudaError_t launch_splitk(GemmCtx& g, const CUtensorMap& ta, const CUtensorMap& tb, int M, const int* m_dev, int m_mul, int N, int K,
+                                 const GemmEpi& epi, cudaStream_t st, int tiles, int splits, int kb_per) {
+  using G = GemmTc<64>;
+  if (!g.sk_attr) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    g.sk_attr = true;
+  }
+  return launch_k(gemm_tc_splitk_kernel, dim3(tiles, splits), dim3(G::THREADS), G::SMEM_BYTES, st, g.pdl, ta, tb, M, m_dev, m_mul, N, K, epi,
+                  g.sk_ws, g.sk_cnt, kb_per);
+}
+
 static cudaError_t launch_tc2(GemmCtx& g, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, const int* m_dev, int m_mul,
                               int N, int K, const GemmEpi& epi, cudaStream_t st) {
   using G = GemmTc2;
@@ -147,7 +179,7 @@ static cudaError_t launch_tc2(GemmCtx& g, const CUtensorMap& ta, const CUtensorM
   return launch_k(gemm_tc2_kernel, dim3(2 * clusters), dim3(G::THREADS), G::SMEM_BYTES, st, g.pdl, ta, tb, tc, M, m_dev, m_mul, N, K, epi);
 }
 
-// dtype: 0 bf16, 1 fp32.  impl: DEER_GEMM_* (2 = force the 1-CTA tcgen05 kernel, for A/B comparisons).  a_rows: allocated rows of A (>= M) for the TMA bounds.
+// dtype: 0 bf16, 1 fp32.  impl: DEER_GEMM_* (2 = force the 1-CTA tcgen05 kernels, 3 = those with split-K allowed; for A/B comparisons).  a_rows: allocated rows of A (>= M) for the TMA bounds.
 static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int a_rows, const void* W, int ldw, int M, int N, int K,
                     const GemmEpi& epi, const int* m_dev, int m_mul, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return DEER_OK;
@@ -182,14 +214,14 @@ static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int
     int BN;
     bool use2;
     if (old_pick) {
-      use2 = (impl != 2) && N >= 256 && ((M + 255) / 256) * ((N + 255) / 256) >= 32;
+      use2 = (impl != 2 && impl != 3) && N >= 256 && ((M + 255) / 256) * ((N + 255) / 256) >= 32;
       if (use2) BN = 128;
       else if (mt * ((N + 255) / 256) >= 2 * DEER_NUM_SMS && N >= 256) BN = 256;
       else if (mt * ((N + 127) / 128) >= DEER_NUM_SMS && N >= 128) BN = 128;
       else BN = 64;
     } else {
       const double best1 = std::min(c256, std::min(c128, c64));
-      use2 = (impl != 2) && c2 <= best1;
+      use2 = (impl != 2 && impl != 3) && c2 <= best1;
       if (use2) BN = 128;                     // B box = this CTA's 128-row half of the 256-wide tile
       else BN = (c256 <= c128 && c256 <= c64) ? 256 : (c128 <= c64 ? 128 : 64);
     }
@@ -229,7 +261,26 @@ static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int
     }
     else if (BN == 256) e = launch_tc<256>(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st, 0);
     else if (BN == 128) e = launch_tc<128>(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st, 1);
-    else e = launch_tc<64>(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st, 2);
+    else {
+      // Few tiles on 148 SMs (a 1-4 episode step: M <= 128 rows): splitting K over the idle SMs opens more TMA pipelines on the
+      // weight matrix (llm.down at 32 rows: 33 -> 16 us, profiles/r02_splitk.txt).  OPT-IN (DEER_GEMM_SPLITK=1, or impl 3 through
+      // deer_op_gemm): the partial sums change the fp32 summation order over K, so an episode's bits would depend on how many
+      // episodes share its step -- the default keeps results bit-identical across batch sizes and shardings, and the whole 1-episode
+      // step gains only 2.4 % (it is launch-latency bound).  A split must stream >= 8 k-blocks (>= 16 above 64 rows: the
+      // workspace round trip grows with the rows) or the reduction costs more than it saves.
+      static const bool splitk_on = getenv("DEER_GEMM_SPLITK") ? atoi(getenv("DEER_GEMM_SPLITK")) != 0 : false;
+      const int tiles = mt * ((N + 63) / 64), num_kb = (K + 63) / 64;
+      int splits = std::min(DEER_NUM_SMS / std::max(1, tiles), num_kb / (M <= 64 ? 8 : 16));
+      int kb_per = 0;
+      if ((splitk_on || impl == 3) && g.sk_ws != nullptr && splits >= 2 && tiles <= 256 && (N % 8) == 0) {
+        kb_per = (num_kb + splits - 1) / splits;
+        splits = (num_kb + kb_per - 1) / kb_per;
+      }
+      if (kb_per > 0 && splits >= 2 && size_t(splits) * M * N * sizeof(float) <= g.sk_ws_bytes)
+        e = launch_splitk(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st, tiles, splits, kb_per);
+      else
+        e = launch_tc<64>(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st, 2);
+    }
   }
   if (g.profile) { cudaEventRecord(rec.e1, st); g.recs.push_back(rec); }
   if (e != cudaSuccess) return set_err(g.err, DEER_E_CUDA, "GEMM launch failed: %s", cudaGetErrorString(e));
@@ -591,6 +642,10 @@ extern "C" int deer_create(const deer_config* cfg, int device, deer_ctx** out) {
   c->vit_chunk = getenv("DEER_VIT_CHUNK") ? atoi(getenv("DEER_VIT_CHUNK")) : 0;
   c->gemm.stats = &c->stats;
   c->gemm.err = &c->err;
+  if (c->dtype == 0 && !c->gemm.alloc_splitk()) {
+    r = set_err(&c->err, DEER_E_CUDA, "split-K workspace allocation failed");
+    g_last_error = c->err; deer_destroy(c); return r;
+  }
   const deer_config& f = c->cfg;
   const size_t B = f.max_batch, NI = 2 * B, S = f.max_seq, D = f.d_model, Wd = f.vit_width, es = c->es;
   const size_t L = c->L, np = c->np, nl = c->nl, H = f.lstm_hidden, LL = f.lstm_layers;
@@ -691,6 +746,7 @@ extern "C" void deer_destroy(deer_ctx* c) {
   if (c->h_nact) cudaFreeHost(c->h_nact);
   for (auto& r : c->gemm.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto e : c->gemm.pool) cudaEventDestroy(e);
+  c->gemm.free_splitk();
   if (c->ev_step0) cudaEventDestroy(c->ev_step0);
   if (c->ev_step1) cudaEventDestroy(c->ev_step1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -1712,6 +1768,7 @@ extern "C" int deer_op_gemm(int impl, int dtype, const void* A, int lda, const v
                             void* stream) {
   if (!A || !W || !C) return set_err(nullptr, DEER_E_INVALID, "null pointer");
   g_op_gemm.err = &g_op_err;
+  if (dtype == 0) g_op_gemm.alloc_splitk();             // best effort: without the workspace the few-row launches stay one CTA per tile
   static int dbg = getenv("DEER_EPI_DBG") ? atoi(getenv("DEER_EPI_DBG")) : 0;
   GemmEpi e{C, ldc, dtype == 1 ? 1 : out_f32, bias, act, scale, resid, ldc, dbg};
   int r = run_gemm(g_op_gemm, impl, dtype, A, lda, M, W, ldw, M, N, K, e, m_dev, m_mul, reinterpret_cast<cudaStream_t>(stream));

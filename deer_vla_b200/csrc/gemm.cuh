@@ -382,6 +382,153 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Split-K variant of the 128 x 64 kernel for the few-row GEMMs of a 1-4 episode step (M <= 128 token rows x N = 2048:
+// 32 tiles on 148 SMs).  Those launches stream their weight matrix once and are bound by the bytes in flight, i.e. by
+// how many SMs have a TMA pipeline open; grid = (tiles, splits) puts `splits` CTAs on each tile, each accumulating
+// kb_per k-blocks in TMEM and writing its fp32 partial tile to a workspace.  The last CTA to arrive on the tile's
+// counter (threadfence + atomic) sums the partials IN SPLIT ORDER -- the result does not depend on which CTA is last
+// -- and runs the ordinary epilogue; it also re-arms the counter for the next launch.
+// ws: [splits, M_host, N] fp32.  counters: one int per tile, zero between launches.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GemmTc<64>::THREADS, 1)
+gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      int M_host, const int* __restrict__ m_dev, int m_mul, int N, int K, GemmEpi epi,
+                      float* __restrict__ ws, int* __restrict__ counters, int kb_per) {
+  constexpr int BN = 64;
+  using G = GemmTc<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G::STAGES * G::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + G::STAGES;
+  uint64_t* tfull_bar = empty_bar + G::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < G::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+  const int M = dyn_rows(M_host, m_dev, m_mul);
+  const int n_blocks = (N + BN - 1) / BN;
+  const int tile = blockIdx.x, split = blockIdx.y, splits = gridDim.y;
+  const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+  const int num_kb = (K + G::BK - 1) / G::BK;
+  const int kb0 = split * kb_per;
+  const int kb1 = min(num_kb, kb0 + kb_per);          // the host sizes `splits` so that every split owns >= 1 k-block
+  const bool live = m_blk * G::BM < M;                // tiles past the device-side row count: all of their splits skip alike
+
+  if (warp == 0) {
+    if (lane == 0 && live) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint8_t* sa = smem + s * G::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], G::STAGE_BYTES);
+        tma_load_2d(sa, &tmA, &full_bar[s], kb * G::BK, m_blk * G::BM);
+        tma_load_2d(sa + G::A_BYTES, &tmB, &full_bar[s], kb * G::BK, n_blk * BN);
+        if (++s == G::STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && live) {
+      constexpr uint32_t idesc = make_idesc_bf16(G::BM, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * G::STAGE_BYTES);
+        const uint64_t adesc = make_desc_sw128(a_addr);
+        const uint64_t bdesc = make_desc_sw128(a_addr + G::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < G::BK / G::UMMA_K; ++k)
+          umma_bf16(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+        if (++s == G::STAGES) { s = 0; ph ^= 1u; }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else if (live) {
+    // ===== epilogue warps: TMEM -> fp32 partial tile in the workspace; the tile's last CTA reduces and stores =====
+    const int lane_grp = warp & 3;
+    const int col_half = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;                    // 0..255 among the epilogue threads
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const int row = m_blk * G::BM + lane_grp * 32 + lane;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
+    {
+      float v[32];
+      tmem_ld_32x32(taddr + static_cast<uint32_t>(col_half * 32), v);
+      tmem_ld_wait();
+      const int col0 = n_blk * BN + col_half * 32;
+      if (row < M && col0 < N) {                       // N % 8 == 0 (host): an 8-column group is inside or outside as a whole
+        float* wp = ws + (static_cast<size_t>(split) * M_host + row) * N + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          if (col0 + j < N) __stcg(reinterpret_cast<float4*>(wp + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+      }
+    }
+    __threadfence();                                    // partial tile visible device-wide before the arrival below
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (et == 0) {
+      __threadfence();
+      const int old = atomicAdd(&counters[tile], 1);
+      const int last = (old == splits - 1);
+      if (last) counters[tile] = 0;                     // re-armed for the next launch (stream order)
+      *last_flag = last;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (*last_flag) {
+      __threadfence();
+      const float sc = (epi.scale != nullptr) ? __ldg(epi.scale) : 1.0f;
+      const int rows_here = min(G::BM, M - m_blk * G::BM);
+      for (int idx = et; idx < rows_here * (BN / 8); idx += 256) {
+        const int r = m_blk * G::BM + idx / (BN / 8);
+        const int col0 = n_blk * BN + (idx % (BN / 8)) * 8;
+        if (col0 >= N) continue;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        const float* wp = ws + static_cast<size_t>(r) * N + col0;
+        const size_t sstride = static_cast<size_t>(M_host) * N;
+#pragma unroll 4
+        for (int s = 0; s < splits; ++s) {
+          const float4 p0 = __ldcg(reinterpret_cast<const float4*>(wp + s * sstride));
+          const float4 p1 = __ldcg(reinterpret_cast<const float4*>(wp + s * sstride + 4));
+          v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
+          v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+        }
+        epi_store<8, true>(epi, sc, r, col0, N, v);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // 2-CTA tcgen05 GEMM (cta_group::2): a CTA pair (cluster of 2, same TPC) computes a 256 x 256 tile.
 // Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 N-rows), so shared-memory
 // fill + operand-read traffic per SM is 2/3 of the 1-CTA kernel's and the L2->SM traffic per FLOP halves

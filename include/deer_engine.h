@@ -35,7 +35,8 @@ enum {
 enum { DEER_PREC_BF16 = 0,   /* product path: bf16 operands, tcgen05 tensor cores, fp32 accumulate */
        DEER_PREC_FP32 = 1 }; /* validation path: fp32 everywhere, CUDA-core GEMMs (slow) */
 
-enum { DEER_GEMM_TCGEN05 = 0, DEER_GEMM_SIMT = 1 };   /* SIMT = debug fallback selector for bf16 */
+enum { DEER_GEMM_TCGEN05 = 0, DEER_GEMM_SIMT = 1,      /* SIMT = debug fallback selector for bf16 */
+       DEER_GEMM_TC_1CTA = 2, DEER_GEMM_TC_SPLITK = 3 };   /* deer_op_gemm A/B selectors: no 2-CTA kernel / and split-K for few-row launches */
 
 enum { DEER_THR_L2 = 0, DEER_THR_MEAN = 1, DEER_THR_MAX = 2, DEER_THR_COSINE = 3 }; /* value_net.py:105-117 */
 

@@ -34,7 +34,7 @@ only = sys.argv[2] if len(sys.argv) > 2 else None
 if only and only != "all":
     SHAPES = [x for x in SHAPES if x[0] == only]
 res = {}
-print("impl", impl, "(0 = auto: 2-CTA when eligible, 2 = force 1-CTA)")
+print("impl", impl, "(0 = auto: 2-CTA when eligible, 2 = force 1-CTA, 3 = 1-CTA with split-K for few-row launches)")
 for name, M, N, K, act, resid in SHAPES:
     A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
     W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()

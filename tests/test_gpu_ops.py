@@ -273,3 +273,33 @@ def test_gemm_tma_store_epilogue_is_bit_identical(M, N, K, act):
         assert torch.equal(a.view(torch.int16), b.view(torch.int16))
     ref = _ref_gemm(A, W, bias, act, None, None)
     assert (outs["1"][0].float() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K", [(32, 2048, 8192), (32, 2048, 2048), (1, 512, 2048), (128, 1024, 4096), (97, 520, 2000), (130, 256, 2048)])
+@pytest.mark.parametrize("mode", ["bf16", "f32_resid", "bias_gelu"])
+def test_gemm_split_k_for_few_row_launches(M, N, K, mode):
+    """Few tiles on 148 SMs (1-4 episode steps): the OPT-IN split-K kernel (fp32 partial tiles in a workspace, the tile's last CTA
+    reduces in split order and runs the ordinary epilogue) against the one-CTA-per-tile launch of the same 128x64 kernel.  The two differ
+    only in the fp32 summation order over K (one TMEM accumulation vs `splits` partial sums), so they agree to fp32 rounding of the
+    accumulator -- bar 2e-5 of the output scale before the bf16 store, one bf16 ulp after it -- and the split-K result is
+    BIT-reproducible run to run (the reduction order does not depend on which CTA arrives last).  Ragged N / K and a second row
+    tile (M = 130) included; the counters re-arm themselves (three launches in a row)."""
+    from deer_vla_b200.engine import op_gemm
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    kw = {"bf16": dict(), "f32_resid": dict(bias=bias, resid=resid), "bias_gelu": dict(bias=bias, act=1)}[mode]
+    runs = [op_gemm(A, W, impl="tcgen05_splitk", **kw).clone() for _ in range(3)]
+    base = op_gemm(A, W, impl="tcgen05_1cta", **kw).clone()
+    torch.cuda.synchronize()
+    for r in runs[1:]:
+        assert torch.equal(r.view(torch.int32 if r.dtype == torch.float32 else torch.int16), runs[0].view(torch.int32 if r.dtype == torch.float32 else torch.int16))
+    ref = _ref_gemm(A, W, kw.get("bias"), kw.get("act", 0), None, kw.get("resid"))
+    scale = max(1.0, ref.abs().max().item())
+    if runs[0].dtype == torch.float32:
+        assert (runs[0] - base).abs().max().item() <= 2e-5 * scale
+    else:
+        assert (runs[0].float() - base.float()).abs().max().item() <= 2.0 ** -7 * scale      # one bf16 ulp at the output scale
+    assert (runs[0].float() - ref).abs().max().item() <= 1e-2 * scale
