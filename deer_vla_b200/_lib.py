@@ -74,6 +74,7 @@ SYMBOLS = {
     "deer_get_tap": (C.c_int, [_P, C.c_char_p, C.c_int, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "deer_get_stats": (C.c_int, [_P, C.POINTER(DeerStats)]),
     "deer_set_launch_overlap": (C.c_int, [C.c_int]),
+    "deer_set_row_order": (C.c_int, [C.c_int]),
     "deer_set_profile": (C.c_int, [_P, C.c_int]),
     "deer_get_profile": (C.c_int, [_P, C.POINTER(DeerProfile)]),
     "deer_op_gemm": (C.c_int, [C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int,

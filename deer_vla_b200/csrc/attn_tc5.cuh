@@ -44,7 +44,7 @@ static_assert(AttnTc5::SMEM_BYTES <= 227 * 1024, "attn_tc5 shared memory");
 __global__ void __launch_bounds__(AttnTc5::THREADS, 1)
 attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                 const bf16* __restrict__ Qg, int ldq, bf16* __restrict__ Og, int ldo, int B, int H, int Sq, int Sk, float scale_log2,
-                long long* __restrict__ dbg) {
+                long long* __restrict__ dbg, int rev) {
   using A = AttnTc;
   using A5 = AttnTc5;
   extern __shared__ uint8_t smem_raw[];
@@ -72,6 +72,9 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int pv_steps = (n_mma + 15) / 16;
   const int my_items = (n_items > static_cast<int>(blockIdx.x)) ? (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
   const int total = my_items * n_sub;                     // query tiles this CTA processes, in order
+  // rev: walk the (image, head) items from the LAST image down -- the q/k/v rows the preceding GEMM wrote last are still in L2,
+  // and the rows written last here are the ones the following GEMM reads first ("snake" order)
+  auto item_of = [&](int is) { const int i = static_cast<int>(blockIdx.x) + is * static_cast<int>(gridDim.x); return rev ? n_items - 1 - i : i; };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -99,7 +102,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ===== TMA producer: K/V once per item (double buffered across items), Q once per tile =====
     if (lane == 0) {
       for (int is = 0; is < my_items; ++is) {
-        const int it = blockIdx.x + is * gridDim.x;
+        const int it = item_of(is);
         const int b = it / H, h = it % H;
         const int kb = is & 1;
         mbar_wait(&kv_empty[kb], ((is >> 1) & 1) ^ 1u);
@@ -280,7 +283,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       TICK5(1);
       // ---- output of this tile: (O + tail keys) / l -> bf16 -> staging -> row-contiguous global stores.  The other group
       // keeps the SM busy while this one waits for the PV MMA.
-      const int it = blockIdx.x + is * gridDim.x;
+      const int it = item_of(is);
       const int b = it / H, h = it - b * H;
       const float inv = 1.0f / l;
       mbar_wait(&o_full[u], par);
@@ -349,7 +352,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ===== spare warp: the few query rows that do not fill a 128-row tile, on CUDA cores, against the smem K/V =====
     float* pbuf = reinterpret_cast<float*>(smem + A5::OFF_P);
     for (int is = 0; is < my_items; ++is) {
-      const int it = blockIdx.x + is * gridDim.x;
+      const int it = item_of(is);
       const int b = it / H, h = it % H, kb = is & 1;
       mbar_wait(&kv_full[kb], (is >> 1) & 1);
       const uint8_t* sK = smem + A5::OFF_K + kb * A::KV_BYTES;

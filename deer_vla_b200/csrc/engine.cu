@@ -77,6 +77,10 @@ static bool make_tmap_c(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_
 
 // Launch with (optionally) programmatic stream serialization: the kernel may begin while its predecessor drains; the kernels
 // launched this way all start with pdl_wait() (common.cuh).  DEER_PDL=0 turns it off (A/B), and it is never used during graph capture.
+// "Snake" traversal: the streaming kernels between two GEMMs (LayerNorm rows, ViT attention items) walk their rows from the END, i.e.
+// they start on what the producing GEMM wrote last (still in the 126 MB L2) and finish on what the consuming GEMM reads first.
+// Row-independent kernels: results are bit-identical either way (DEER_SNAKE=0 for the A/B).
+static bool g_snake = getenv("DEER_SNAKE") ? atoi(getenv("DEER_SNAKE")) != 0 : true;
 static bool g_launch_overlap = getenv("DEER_PDL") ? atoi(getenv("DEER_PDL")) != 0 : true;
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
@@ -326,7 +330,7 @@ static int run_attention(int impl, int dtype, const AttnParams& p, std::string* 
       }
       const int grid = std::min(p.B_host * p.H, DEER_NUM_SMS);
       launch_k(attn_tc5_kernel, dim3(grid), dim3(AttnTc5::THREADS), AttnTc5::SMEM_BYTES, st, pdl, *tq, *tk, *tv, reinterpret_cast<const bf16*>(p.Q), p.ldq,
-               reinterpret_cast<bf16*>(p.O), p.ldo, p.B_host, p.H, p.Sq, p.Sk, p.scale * 1.4426950408889634f, g_attn_dbg);
+               reinterpret_cast<bf16*>(p.O), p.ldo, p.B_host, p.H, p.Sq, p.Sk, p.scale * 1.4426950408889634f, g_attn_dbg, g_snake ? 1 : 0);
       done = true;
     }
   }
@@ -1115,7 +1119,7 @@ template <typename T> struct StepImpl {
     const bool vec_ok = (D % 128 == 0) && (in_ld % 4 == 0) && (out_ld % 4 == 0) && (out2 == nullptr || out2_ld % 4 == 0);
     const int nvec = D / 128;
     const int wgrid = (rows + 3) / 4;
-#define LNW(NV) launch_k(layernorm_warp_kernel<TIn, TOut, NV>, dim3(wgrid), dim3(128), 0, st, c->gemm.pdl, in, in_ld, in_map, g, b, groups, out, out_ld, map, out2, out2_ld, relu, rows, n_dev, n_mul)
+#define LNW(NV) launch_k(layernorm_warp_kernel<TIn, TOut, NV>, dim3(wgrid), dim3(128), 0, st, c->gemm.pdl, in, in_ld, in_map, g, b, groups, out, out_ld, map, out2, out2_ld, relu, rows, n_dev, n_mul, g_snake ? 1 : 0)
     if (vec_ok && nvec == 1) LNW(1);
     else if (vec_ok && nvec == 2) LNW(2);
     else if (vec_ok && nvec == 4) LNW(4);
@@ -1706,6 +1710,12 @@ extern "C" int deer_get_tap(deer_ctx* c, const char* name, int layer, float* out
 extern "C" int deer_set_launch_overlap(int enable) {
   const int prev = g_launch_overlap ? 1 : 0;
   g_launch_overlap = enable != 0;
+  return prev;
+}
+
+extern "C" int deer_set_row_order(int snake) {
+  const int prev = g_snake ? 1 : 0;
+  g_snake = snake != 0;
   return prev;
 }
 

@@ -131,14 +131,15 @@ template <typename TIn, typename TOut, int NVEC>
 __global__ void __launch_bounds__(128)
 layernorm_warp_kernel(const TIn* in, int in_ld, LnMap in_map, const float* __restrict__ gamma, const float* __restrict__ beta,
                       int groups, TOut* out, int out_ld, LnMap map, TOut* out2, int out2_ld,
-                      int relu, int rows_host, const int* __restrict__ n_dev, int n_mul) {
+                      int relu, int rows_host, const int* __restrict__ n_dev, int n_mul, int rev) {
   constexpr int D = NVEC * 128;
   pdl_wait();
   pdl_trigger();
   const int rows = dyn_rows(rows_host, n_dev, n_mul);
   const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (r >= rows) return;
+  if (rev) r = rows - 1 - r;          // last rows first: they are what the producing GEMM left in L2 ("snake" order)
   const TIn* x = in + ln_out_row(r, in_map) * in_ld;
   float4 v[NVEC];
   float s = 0.0f;

@@ -110,6 +110,11 @@ class DeerEngine:
         """Process-wide switch of programmatic dependent launch (see include/deer_engine.h); returns the previous setting."""
         return bool(_lib.load().deer_set_launch_overlap(int(enable)))
 
+    @staticmethod
+    def set_row_order(snake: bool) -> bool:
+        """Process-wide switch of the "snake" row order of LayerNorm / ViT attention (see include/deer_engine.h); returns the previous setting."""
+        return bool(_lib.load().deer_set_row_order(int(snake)))
+
     def set_profile(self, enable: bool):
         self._check(self.lib.deer_set_profile(self._h, int(enable)))
 

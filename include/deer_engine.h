@@ -190,6 +190,12 @@ int deer_get_profile(deer_ctx* ctx, deer_profile* out);
  * Environment DEER_PDL=0/1 sets the initial value. */
 int deer_set_launch_overlap(int enable);
 
+/* Row order of the streaming kernels that sit between two GEMMs (process-wide): 1 (default) = LayerNorm rows and ViT attention
+ * items are walked from the END ("snake" order): they start on the rows the producing GEMM wrote last, which the 126 MB L2 still
+ * holds, and finish on the rows the consuming GEMM reads first.  The kernels are row-independent, so results are bit-identical
+ * either way (tested); returns the previous setting.  Environment DEER_SNAKE=0/1 sets the initial value. */
+int deer_set_row_order(int snake);
+
 /* One frame of the threshold-calibration pass in the reference's TRAINING layout -- replaces generate_action_values
  * (value_net.py:300-399): MPTFlamingo.forward(return_in_feat, only_extra_exit) over windows of frames (flamingo_mpt.py:476-492)
  * followed by ActionValueNet.forward(mode='generate') (value_net.py:134-160).  Call it for frames t = 0 .. window-2 of n

@@ -362,6 +362,38 @@ def test_full3b_launch_overlap_is_bit_identical(full3b, gold_full):
     eng.close()
 
 
+def test_full3b_snake_row_order_is_bit_identical(full3b, gold_full):
+    """LayerNorm rows and ViT attention items are walked from the END by default, so that they start on what the producing GEMM left
+    in L2 (deer_set_row_order, include/deer_engine.h).  The kernels are row-independent: three consecutive 3B steps of 8 episodes
+    (carried LSTM state, compaction after every exit) give bit-identical poses, grippers, deltas and exit layers in both orders."""
+    from deer_vla_b200.engine import DeerEngine
+    ocfg, W = full3b
+    S = int(gold_full["S"])
+    thr = gold_full["thresholds_B"].tolist()
+    eng = _engine(ocfg, W, max_batch=8, max_seq=S, precision="bf16")
+    eng.set_thresholds(thr)
+    eps = list(range(8))
+    runs = {}
+    prev = DeerEngine.set_row_order(True)
+    try:
+        for mode in (True, False):
+            DeerEngine.set_row_order(mode)
+            eng.reset()
+            outs = []
+            for t in range(3):
+                rgb, grip, ids = _inputs(ocfg, eps, t, S)
+                o = eng.step(rgb.cuda(), grip.cuda(), ids.cuda())
+                outs.append({k: v.cpu().clone() for k, v in o.items()})
+            runs[mode] = outs
+    finally:
+        DeerEngine.set_row_order(prev)
+    for a, b in zip(runs[True], runs[False]):
+        for k in ("pose", "gripper", "exit_layer", "delta"):
+            if a.get(k) is not None:
+                assert torch.equal(torch.nan_to_num(a[k].float(), nan=-7.0), torch.nan_to_num(b[k].float(), nan=-7.0)), k
+    eng.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # OpenFlamingo-9B size (BASELINE configs[3])
 # ------------------------------------------------------------------------------------------------
