@@ -109,7 +109,7 @@ struct LaunchStats {
 struct GemmRec { cudaEvent_t e0, e1; int tag, epoch, m_host, m_mul, n, k; bool dyn; int in_es, out_es; bool has_res; };
 struct GemmCtx {
   std::map<TmapKey, CUtensorMap> tmaps;
-  bool attr_set[4] = {false, false, false, false};
+  bool attr_set[5] = {false, false, false, false, false};
   LaunchStats* stats = nullptr;
   std::string* err = nullptr;
   bool pdl = false;            // programmatic dependent launch allowed (off while a CUDA graph is being captured)
@@ -144,18 +144,18 @@ struct GemmCtx {
   }
 };
 
-template <int BN>
+template <int BN, int BM = 128>
 static cudaError_t launch_tc(GemmCtx& g, const CUtensorMap& ta, const CUtensorMap& tb, int M, const int* m_dev, int m_mul, int N, int K,
                              const GemmEpi& epi, cudaStream_t st, int idx) {
-  using G = GemmTc<BN>;
+  using G = GemmTc<BN, BM>;
   if (!g.attr_set[idx]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     g.attr_set[idx] = true;
   }
-  const int tiles = ((M + 127) / 128) * ((N + BN - 1) / BN);
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = std::max(1, std::min(tiles, DEER_NUM_SMS));
-  return launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(G::THREADS), G::SMEM_BYTES, st, g.pdl, ta, tb, M, m_dev, m_mul, N, K, epi);
+  return launch_k(gemm_tc_kernel<BN, BM>, dim3(grid), dim3(G::THREADS), G::SMEM_BYTES, st, g.pdl, ta, tb, M, m_dev, m_mul, N, K, epi);
 }
 
 static cudaError_t launch_splitk(GemmCtx& g, const CUtensorMap& ta, const CUtensorMap& tb, int M, const int* m_dev, int m_mul, int N, int K,
@@ -183,7 +183,7 @@ static cudaError_t launch_tc2(GemmCtx& g, const CUtensorMap& ta, const CUtensorM
   return launch_k(gemm_tc2_kernel, dim3(2 * clusters), dim3(G::THREADS), G::SMEM_BYTES, st, g.pdl, ta, tb, tc, M, m_dev, m_mul, N, K, epi);
 }
 
-// dtype: 0 bf16, 1 fp32.  impl: DEER_GEMM_* (2 = force the 1-CTA tcgen05 kernels, 3 = those with split-K allowed; for A/B comparisons).  a_rows: allocated rows of A (>= M) for the TMA bounds.
+// dtype: 0 bf16, 1 fp32.  impl: DEER_GEMM_* (2 = force the 1-CTA tcgen05 kernels, 3 = 128-row tiles with split-K allowed, 4 = 128-row tiles only; for A/B comparisons).  a_rows: allocated rows of A (>= M) for the TMA bounds.
 static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int a_rows, const void* W, int ldw, int M, int N, int K,
                     const GemmEpi& epi, const int* m_dev, int m_mul, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return DEER_OK;
@@ -214,27 +214,34 @@ static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int
     const double c256 = (N >= 256) ? waves((long)mt * ((N + 255) / 256), DEER_NUM_SMS) * 32768.0 / 0.83 : 1e30;
     const double c128 = (N >= 128) ? waves((long)mt * ((N + 127) / 128), DEER_NUM_SMS) * 16384.0 / 0.75 : 1e30;
     const double c64 = waves((long)mt * ((N + 63) / 64), DEER_NUM_SMS) * 8192.0 / 0.55;
+    // 64 x 64 tiles (tcgen05.mma M = 64): such launches are bound by the bytes one SM pulls per k-block (16 KB against 24 KB for
+    // 128 x 64), so a tile costs 2/3 of a 128 x 64 tile for half the rows -- it wins when it turns a sparse wave into a full one
+    // (M = 514, N = 1024: 80 -> 144 tiles) and, with 12 stages in flight, on the <= 64-row launches of a 1-2 episode step.
+    const double c6464 = waves((long)((M + 63) / 64) * ((N + 63) / 64), DEER_NUM_SMS) * 8192.0 / 0.55 * (2.0 / 3.0);
     static const bool old_pick = getenv("DEER_GEMM_OLD_PICK") != nullptr;
-    int BN;
+    int BN, BM = 128;
     bool use2;
+    const bool one_cta = impl == 2 || impl == 3 || impl == 4;   // deer_op_gemm A/B selectors (include/deer_engine.h)
     if (old_pick) {
-      use2 = (impl != 2 && impl != 3) && N >= 256 && ((M + 255) / 256) * ((N + 255) / 256) >= 32;
+      use2 = !one_cta && N >= 256 && ((M + 255) / 256) * ((N + 255) / 256) >= 32;
       if (use2) BN = 128;
       else if (mt * ((N + 255) / 256) >= 2 * DEER_NUM_SMS && N >= 256) BN = 256;
       else if (mt * ((N + 127) / 128) >= DEER_NUM_SMS && N >= 128) BN = 128;
       else BN = 64;
     } else {
+      static const bool half_tiles = getenv("DEER_GEMM_M64") ? atoi(getenv("DEER_GEMM_M64")) != 0 : true;
       const double best1 = std::min(c256, std::min(c128, c64));
-      use2 = (impl != 2 && impl != 3) && c2 <= best1;
+      use2 = !one_cta && c2 <= best1;
       if (use2) BN = 128;                     // B box = this CTA's 128-row half of the 256-wide tile
       else BN = (c256 <= c128 && c256 <= c64) ? 256 : (c128 <= c64 ? 128 : 64);
+      if (!use2 && half_tiles && impl != 3 && impl != 4 && c6464 < (one_cta ? best1 : std::min(best1, c2))) { BN = 64; BM = 64; }
     }
-    TmapKey ka{A, (uint64_t)a_rows, (uint64_t)K, (uint64_t)lda, 128u};
+    TmapKey ka{A, (uint64_t)a_rows, (uint64_t)K, (uint64_t)lda, (uint32_t)BM};
     TmapKey kb{W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)BN};
     auto ia = g.tmaps.find(ka);
     if (ia == g.tmaps.end()) {
       CUtensorMap tm;
-      if (!make_tmap(&tm, A, a_rows, K, lda, 128)) return set_err(g.err, DEER_E_CUDA, "cuTensorMapEncodeTiled failed for A (%d x %d ld %d)", a_rows, K, lda);
+      if (!make_tmap(&tm, A, a_rows, K, lda, BM)) return set_err(g.err, DEER_E_CUDA, "cuTensorMapEncodeTiled failed for A (%d x %d ld %d)", a_rows, K, lda);
       ia = g.tmaps.emplace(ka, tm).first;
     }
     auto ib = g.tmaps.find(kb);
@@ -265,6 +272,7 @@ static int run_gemm(GemmCtx& g, int impl, int dtype, const void* A, int lda, int
     }
     else if (BN == 256) e = launch_tc<256>(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st, 0);
     else if (BN == 128) e = launch_tc<128>(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st, 1);
+    else if (BM == 64) e = launch_tc<64, 64>(g, ia->second, ib->second, M, m_dev, m_mul, N, K, epi, st, 4);
     else {
       // Few tiles on 148 SMs (a 1-4 episode step: M <= 128 rows): splitting K over the idle SMs opens more TMA pipelines on the
       // weight matrix (llm.down at 32 rows: 33 -> 16 us, profiles/r02_splitk.txt).  OPT-IN (DEER_GEMM_SPLITK=1, or impl 3 through

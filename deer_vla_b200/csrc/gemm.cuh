@@ -238,27 +238,33 @@ __device__ __forceinline__ void epi_store(const GemmEpi& e, float sc, int row, i
 // ---------------------------------------------------------------------------------------------
 // tcgen05 GEMM
 // ---------------------------------------------------------------------------------------------
-template <int BN>
+// BM_ = 64: half-height tiles (tcgen05.mma M = 64: accumulator row r sits in TMEM lane (r % 16) + 32 * (r / 16), i.e. the first 16
+// lanes of every lane quarter) for launches whose 128-row tiles would fill fewer than half of the SMs (a 1-episode ViT: M = 514
+// rows x N = 1024 -> 80 tiles of 128 x 64 but 144 of 64 x 64).  Such launches are bound by what ONE SM can pull through its TMA
+// pipeline per k-block (24 KB for a 128 x 64 tile, 16 KB for 64 x 64, and 12 stages instead of 8 in flight), not by the tensor
+// pipe, which M = 64 runs at half rate.  K is accumulated in the same order: results are bit-identical to the 128-row tiles.
+template <int BN, int BM_ = 128>
 struct GemmTc {
-  static constexpr int BM = 128;
+  static constexpr int BM = BM_;
   static constexpr int BK = 64;                       // 64 bf16 = one 128B swizzle row
   static constexpr int UMMA_K = 16;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BM == 64) ? 12 : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = 2 * BN;            // two accumulator buffers (128 / 256 / 512 columns)
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual 1 KiB alignment
   static constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quarter, each owning half of the columns
   static constexpr int THREADS = 64 + 32 * EPI_WARPS; // warp0 TMA, warp1 MMA+TMEM alloc, warps2-9 epilogue
+  static constexpr int ROWS_PER_QUARTER = BM / 4;     // accumulator rows held by one TMEM lane quarter (32, or 16 for BM = 64)
 };
 
-template <int BN>
-__global__ void __launch_bounds__(GemmTc<BN>::THREADS, 1)
+template <int BN, int BM_ = 128>
+__global__ void __launch_bounds__(GemmTc<BN, BM_>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M_host, const int* __restrict__ m_dev, int m_mul, int N, int K, GemmEpi epi) {
-  using G = GemmTc<BN>;
+  using G = GemmTc<BN, BM_>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -357,7 +363,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      const int row = m_blk * G::BM + lane_grp * 32 + lane;
+      const int row = m_blk * G::BM + lane_grp * G::ROWS_PER_QUARTER + lane;
+      const bool row_ok = (G::BM == 128 || lane < G::ROWS_PER_QUARTER) && row < M;   // BM = 64: lanes 16-31 of a quarter hold no row
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(as * BN);
 #pragma unroll 1
       for (int c = col_half * CH; c < (col_half + 1) * CH; ++c) {
@@ -365,7 +372,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
         tmem_ld_wait();
         const int col0 = n_blk * BN + c * 32;
-        if (row < M && col0 < N) epi_store<32, true>(epi, sc, row, col0, N, v);
+        if (row_ok && col0 < N) epi_store<32, true>(epi, sc, row, col0, N, v);
       }
       tc_fence_before();
       __syncwarp();

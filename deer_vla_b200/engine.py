@@ -332,7 +332,7 @@ def op_gemm(A: torch.Tensor, W: torch.Tensor, bias=None, act: int = 0, scale=Non
         Cm = torch.zeros(M, N, dtype=odt, device=A.device)
         rp = None
     stream = torch.cuda.current_stream(A.device).cuda_stream
-    rc = lib.deer_op_gemm({"tcgen05": 0, "simt": 1, "tcgen05_1cta": 2, "tcgen05_splitk": 3}[impl], dtype, _ptr(A), A.stride(0), _ptr(W), W.stride(0), _ptr(Cm), Cm.stride(0),
+    rc = lib.deer_op_gemm({"tcgen05": 0, "simt": 1, "tcgen05_1cta": 2, "tcgen05_splitk": 3, "tcgen05_1cta_m128": 4}[impl], dtype, _ptr(A), A.stride(0), _ptr(W), W.stride(0), _ptr(Cm), Cm.stride(0),
                           M, N, K, _ptr(bias), act, _ptr(scale), rp, int(out_f32 or resid is not None), _ptr(m_dev), m_mul,
                           C.c_void_p(stream))
     if rc != 0:

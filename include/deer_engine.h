@@ -36,7 +36,8 @@ enum { DEER_PREC_BF16 = 0,   /* product path: bf16 operands, tcgen05 tensor core
        DEER_PREC_FP32 = 1 }; /* validation path: fp32 everywhere, CUDA-core GEMMs (slow) */
 
 enum { DEER_GEMM_TCGEN05 = 0, DEER_GEMM_SIMT = 1,      /* SIMT = debug fallback selector for bf16 */
-       DEER_GEMM_TC_1CTA = 2, DEER_GEMM_TC_SPLITK = 3 };   /* deer_op_gemm A/B selectors: no 2-CTA kernel / and split-K for few-row launches */
+       DEER_GEMM_TC_1CTA = 2, DEER_GEMM_TC_SPLITK = 3, DEER_GEMM_TC_1CTA_M128 = 4 };   /* deer_op_gemm A/B selectors: no 2-CTA kernel /
+       128-row tiles with split-K for few-row launches / 128-row tiles only (no 64 x 64 tiles, no split-K) */
 
 enum { DEER_THR_L2 = 0, DEER_THR_MEAN = 1, DEER_THR_MAX = 2, DEER_THR_COSINE = 3 }; /* value_net.py:105-117 */
 

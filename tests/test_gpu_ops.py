@@ -292,7 +292,7 @@ def test_gemm_split_k_for_few_row_launches(M, N, K, mode):
     resid = torch.randn(M, N, device="cuda", generator=g)
     kw = {"bf16": dict(), "f32_resid": dict(bias=bias, resid=resid), "bias_gelu": dict(bias=bias, act=1)}[mode]
     runs = [op_gemm(A, W, impl="tcgen05_splitk", **kw).clone() for _ in range(3)]
-    base = op_gemm(A, W, impl="tcgen05_1cta", **kw).clone()
+    base = op_gemm(A, W, impl="tcgen05_1cta_m128", **kw).clone()
     torch.cuda.synchronize()
     for r in runs[1:]:
         assert torch.equal(r.view(torch.int32 if r.dtype == torch.float32 else torch.int16), runs[0].view(torch.int32 if r.dtype == torch.float32 else torch.int16))
@@ -303,3 +303,25 @@ def test_gemm_split_k_for_few_row_launches(M, N, K, mode):
     else:
         assert (runs[0].float() - base.float()).abs().max().item() <= 2.0 ** -7 * scale      # one bf16 ulp at the output scale
     assert (runs[0].float() - ref).abs().max().item() <= 1e-2 * scale
+
+
+@pytest.mark.parametrize("M,N,K", [(514, 1024, 4096), (514, 1024, 1024), (32, 2048, 8192), (1, 512, 2048), (97, 520, 1000), (896, 512, 2048), (130, 264, 72)])
+@pytest.mark.parametrize("mode", ["bf16", "f32_resid", "bias_gelu"])
+def test_gemm_half_height_tiles_are_bit_identical(M, N, K, mode):
+    """64 x 64 tiles (tcgen05.mma M = 64, accumulator row r in TMEM lane (r % 16) + 32 * (r / 16)) for launches whose 128-row tiles
+    leave most SMs idle (a 1-episode ViT: M = 514; the LLM at M = 32): K is accumulated in the same order as in the 128-row
+    kernels, so the outputs are BIT-identical to them -- the batch-invariance of the backbone is kept.  Ragged M / N / K included."""
+    from deer_vla_b200.engine import op_gemm
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    kw = {"bf16": dict(), "f32_resid": dict(bias=bias, resid=resid), "bias_gelu": dict(bias=bias, act=1)}[mode]
+    half = op_gemm(A, W, impl="tcgen05_1cta", **kw).clone()          # the cost model picks 64 x 64 tiles for every shape above
+    full = op_gemm(A, W, impl="tcgen05_1cta_m128", **kw).clone()
+    torch.cuda.synchronize()
+    it = torch.int32 if half.dtype == torch.float32 else torch.int16
+    assert torch.equal(half.view(it), full.view(it))
+    ref = _ref_gemm(A, W, kw.get("bias"), kw.get("act", 0), None, kw.get("resid"))
+    assert (half.float() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
