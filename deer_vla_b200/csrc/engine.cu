@@ -1849,6 +1849,14 @@ extern "C" int deer_head_debug(int enable, long long* host_out, int n) {
   return DEER_OK;
 }
 
+#ifdef DEER_GEMM_PROF
+// instrumented build only: per-k-block clock64 of CTA 0 (first tile) of the last gemm_tc_kernel launch
+extern "C" int deer_gemm_debug(long long* host_out, int n) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host_out, g_gemm_prof, std::min(n, 4 * 256) * sizeof(long long)) == cudaSuccess ? DEER_OK : DEER_E_CUDA;
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // on-device image transform
 // ---------------------------------------------------------------------------------------------

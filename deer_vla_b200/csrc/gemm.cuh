@@ -102,6 +102,20 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
+// One lane of a CONVERGED warp.  The single-thread tcgen05 / TMA instructions run on the uniform datapath; issued from a branch the
+// compiler cannot prove single-threaded (`if (lane == 0)`) every one of them is wrapped in an ELECT / BRA.U.ANY serialisation loop
+// (~70 cycles per tcgen05.mma, measured: profiles/r02_mma_issue.txt), issued under elect.sync it is a plain predicated instruction.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -260,6 +274,14 @@ struct GemmTc {
   static constexpr int ROWS_PER_QUARTER = BM / 4;     // accumulator rows held by one TMEM lane quarter (32, or 16 for BM = 64)
 };
 
+#ifdef DEER_GEMM_PROF
+// instrumented build only (scripts/gemm_kblock_prof.sh): clock64 of CTA 0's producer / MMA threads per k-block of its first tile
+__device__ long long g_gemm_prof[4 * 256];
+#define GEMM_PROF(slot, kb) do { if (blockIdx.x == 0 && tile == 0 && (kb) < 256) g_gemm_prof[(kb) * 4 + (slot)] = clock64(); } while (0)
+#else
+#define GEMM_PROF(slot, kb) do { } while (0)
+#endif
+
 template <int BN, int BM_ = 128>
 __global__ void __launch_bounds__(GemmTc<BN, BM_>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -304,25 +326,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_kb = (K + G::BK - 1) / G::BK;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer: converged warp, one elected lane issues =====
+    {
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;    // N fastest: the A tile stays hot in L2
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1u);
-          uint8_t* sa = smem + s * G::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[s], G::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[s], kb * G::BK, m_blk * G::BM);
-          tma_load_2d(sa + G::A_BYTES, &tmB, &full_bar[s], kb * G::BK, n_blk * BN);
+          if (elect_one_sync()) {
+            GEMM_PROF(0, kb);
+            uint8_t* sa = smem + s * G::STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[s], G::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, &full_bar[s], kb * G::BK, m_blk * G::BM);
+            tma_load_2d(sa + G::A_BYTES, &tmB, &full_bar[s], kb * G::BK, n_blk * BN);
+            GEMM_PROF(1, kb);
+          }
+          __syncwarp();
           if (++s == G::STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer: the warp stays converged, one elected lane issues (see elect_one_sync) =====
+    {
       constexpr uint32_t idesc = make_idesc_bf16(G::BM, BN);
       int s = 0;
       uint32_t ph = 0;
@@ -338,16 +365,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t a_addr = smem_u32(smem + s * G::STAGE_BYTES);
           const uint64_t adesc = make_desc_sw128(a_addr);
           const uint64_t bdesc = make_desc_sw128(a_addr + G::A_BYTES);
+          if (elect_one_sync()) {
+            GEMM_PROF(2, kb);
 #pragma unroll
-          for (int k = 0; k < G::BK / G::UMMA_K; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in the (addr>>4) field
-            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < G::BK / G::UMMA_K; ++k) {
+              // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in the (addr>>4) field
+              umma_bf16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[s]);                 // frees the smem stage when these MMAs retire
+            GEMM_PROF(3, kb);
           }
-          umma_commit(&empty_bar[s]);                   // frees the smem stage when these MMAs retire
+          __syncwarp();
           if (++s == G::STAGES) { s = 0; ph ^= 1u; }
         }
-        umma_commit(&tfull_bar[as]);                    // accumulator complete -> epilogue
+        if (elect_one_sync()) umma_commit(&tfull_bar[as]);   // accumulator complete -> epilogue
+        __syncwarp();
         if (++as == 2) { as = 0; aph ^= 1u; }
       }
     }
@@ -441,20 +474,23 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const bool live = m_blk * G::BM < M;                // tiles past the device-side row count: all of their splits skip alike
 
   if (warp == 0) {
-    if (lane == 0 && live) {
+    if (live) {                                         // converged warp, one elected lane issues (see elect_one_sync)
       int s = 0;
       uint32_t ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1u);
-        uint8_t* sa = smem + s * G::STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], G::STAGE_BYTES);
-        tma_load_2d(sa, &tmA, &full_bar[s], kb * G::BK, m_blk * G::BM);
-        tma_load_2d(sa + G::A_BYTES, &tmB, &full_bar[s], kb * G::BK, n_blk * BN);
+        if (elect_one_sync()) {
+          uint8_t* sa = smem + s * G::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], G::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[s], kb * G::BK, m_blk * G::BM);
+          tma_load_2d(sa + G::A_BYTES, &tmB, &full_bar[s], kb * G::BK, n_blk * BN);
+        }
+        __syncwarp();
         if (++s == G::STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && live) {
+    if (live) {
       constexpr uint32_t idesc = make_idesc_bf16(G::BM, BN);
       int s = 0;
       uint32_t ph = 0;
@@ -464,13 +500,17 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const uint32_t a_addr = smem_u32(smem + s * G::STAGE_BYTES);
         const uint64_t adesc = make_desc_sw128(a_addr);
         const uint64_t bdesc = make_desc_sw128(a_addr + G::A_BYTES);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < G::BK / G::UMMA_K; ++k)
-          umma_bf16(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb > kb0 || k != 0) ? 1u : 0u);
-        umma_commit(&empty_bar[s]);
+          for (int k = 0; k < G::BK / G::UMMA_K; ++k)
+            umma_bf16(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        __syncwarp();
         if (++s == G::STAGES) { s = 0; ph ^= 1u; }
       }
-      umma_commit(tfull_bar);
+      if (elect_one_sync()) umma_commit(tfull_bar);
+      __syncwarp();
     }
   } else if (live) {
     // ===== epilogue warps: TMEM -> fp32 partial tile in the workspace; the tile's last CTA reduces and stores =====
@@ -800,25 +840,28 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0) {
     // ===== TMA producer (one per CTA): own A rows + own half of B; bytes are accounted on the leader's barrier =====
-    if (lane == 0) {
+    {                                                   // converged warp, one elected lane issues (see elect_one_sync)
       int s = 0;
       uint32_t ph = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1u);
-          uint8_t* sa = smem + s * G::STAGE_BYTES;
-          const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[s]), 0);
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * G::STAGE_BYTES);
-          tma_load_2d_2cta(sa, &tmA, lead_full, kb * G::BK, m_blk * G::BM + static_cast<int>(rank) * 128);
-          tma_load_2d_2cta(sa + G::A_BYTES, &tmB, lead_full, kb * G::BK, n_blk * G::BN + static_cast<int>(rank) * 128);
+          if (elect_one_sync()) {
+            uint8_t* sa = smem + s * G::STAGE_BYTES;
+            const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[s]), 0);
+            if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * G::STAGE_BYTES);
+            tma_load_2d_2cta(sa, &tmA, lead_full, kb * G::BK, m_blk * G::BM + static_cast<int>(rank) * 128);
+            tma_load_2d_2cta(sa + G::A_BYTES, &tmB, lead_full, kb * G::BK, n_blk * G::BN + static_cast<int>(rank) * 128);
+          }
+          __syncwarp();
           if (++s == G::STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: leader CTA only, one thread, drives both SMs' tensor cores =====
-    if (leader && lane == 0) {
+    // ===== MMA issuer: leader CTA only; the warp stays converged, one elected lane drives both SMs' tensor cores =====
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(G::BM, G::BN);
       int s = 0;
       uint32_t ph = 0;
@@ -834,13 +877,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t a_addr = smem_u32(smem + s * G::STAGE_BYTES);
           const uint64_t adesc = make_desc_sw128(a_addr);
           const uint64_t bdesc = make_desc_sw128(a_addr + G::A_BYTES);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < G::BK / G::UMMA_K; ++k)
-            umma_bf16_2cta(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_2cta(&empty_bar[s]);
+            for (int k = 0; k < G::BK / G::UMMA_K; ++k)
+              umma_bf16_2cta(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2cta(&empty_bar[s]);
+          }
+          __syncwarp();
           if (++s == G::STAGES) { s = 0; ph ^= 1u; }
         }
-        umma_commit_2cta(&tfull_bar[as]);
+        if (elect_one_sync()) umma_commit_2cta(&tfull_bar[as]);
+        __syncwarp();
         if (++as == 2) { as = 0; aph ^= 1u; }
       }
     }
