@@ -99,33 +99,42 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   pdl_trigger();
 
   if (warp == 0) {
-    // ===== TMA producer: K/V once per item (double buffered across items), Q once per tile =====
-    if (lane == 0) {
+    // ===== TMA producer: K/V once per item (double buffered across items), Q once per tile.  The warp stays converged and one
+    // elected lane issues (gemm.cuh: elect_one_sync) =====
+    {
       for (int is = 0; is < my_items; ++is) {
         const int it = item_of(is);
         const int b = it / H, h = it % H;
         const int kb = is & 1;
         mbar_wait(&kv_empty[kb], ((is >> 1) & 1) ^ 1u);
-        mbar_arrive_expect_tx(&kv_full[kb], 2 * A::KV_BYTES);
-        uint8_t* sk = smem + A5::OFF_K + kb * A::KV_BYTES;
-        uint8_t* sv = smem + A5::OFF_V + kb * A::KV_BYTES;
-        tma_load_2d(sk, &tmK, &kv_full[kb], h * 64, b * Sk);
-        tma_load_2d(sk + A::HALF_BYTES, &tmK, &kv_full[kb], h * 64, b * Sk + A::HALF_ROWS);
-        tma_load_2d(sv, &tmV, &kv_full[kb], h * 64, b * Sk);
-        tma_load_2d(sv + A::HALF_BYTES, &tmV, &kv_full[kb], h * 64, b * Sk + A::HALF_ROWS);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&kv_full[kb], 2 * A::KV_BYTES);
+          uint8_t* sk = smem + A5::OFF_K + kb * A::KV_BYTES;
+          uint8_t* sv = smem + A5::OFF_V + kb * A::KV_BYTES;
+          tma_load_2d(sk, &tmK, &kv_full[kb], h * 64, b * Sk);
+          tma_load_2d(sk + A::HALF_BYTES, &tmK, &kv_full[kb], h * 64, b * Sk + A::HALF_ROWS);
+          tma_load_2d(sv, &tmV, &kv_full[kb], h * 64, b * Sk);
+          tma_load_2d(sv + A::HALF_BYTES, &tmV, &kv_full[kb], h * 64, b * Sk + A::HALF_ROWS);
+        }
+        __syncwarp();
         for (int t = 0; t < n_sub; ++t) {
           const int n = is * n_sub + t, qb = n & 1;
           mbar_wait(&q_empty[qb], ((n >> 1) & 1) ^ 1u);
-          mbar_arrive_expect_tx(&q_full[qb], A::Q_BYTES);
-          tma_load_2d(smem + A5::OFF_Q + qb * A::Q_BYTES, &tmQ, &q_full[qb], h * 64, b * Sq + t * 128);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&q_full[qb], A::Q_BYTES);
+            tma_load_2d(smem + A5::OFF_Q + qb * A::Q_BYTES, &tmQ, &q_full[qb], h * 64, b * Sq + t * 128);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer.  The two softmax groups are independent, so the issuer must not make one wait for the other: QK(nq) and
     // PV(np) are issued in whichever order their preconditions come true (a fixed QK(n+1)-then-PV(n) order left the group that
-    // had finished its probabilities waiting until the OTHER group had drained its previous tile). =====
-    if (lane == 0) {
+    // had finished its probabilities waiting until the OTHER group had drained its previous tile).  The warp stays converged --
+    // lane 0's barrier tests decide for all lanes -- and one elected lane issues: from a `lane == 0` branch every tcgen05.mma sits in
+    // a serialisation loop (~70 cycles each, 16 PV steps per tile). =====
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16_major(128, A::NMMA, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16_major(128, 64, 0, 1);     // B = V, MN-major
       int nq = 0, np = 0;                                  // next QK / next PV to issue
@@ -134,33 +143,41 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         bool did = false;
         if (nq < total && nq < np + 2) {                   // at most two tiles in flight (two TMEM buffers)
           const int is = nq / n_sub, t = nq - is * n_sub, kb = is & 1, qb = nq & 1, u = nq & 1;
-          const bool ok = (t != 0 || mbar_test(&kv_full[kb], (is >> 1) & 1)) && mbar_test(&q_full[qb], (nq >> 1) & 1) &&
-                          (nq < 2 || mbar_test(&o_empty[u], ((nq >> 1) - 1) & 1));       // the group has drained its previous tile
+          const bool ok0 = (t != 0 || mbar_test(&kv_full[kb], (is >> 1) & 1)) && mbar_test(&q_full[qb], (nq >> 1) & 1) &&
+                           (nq < 2 || mbar_test(&o_empty[u], ((nq >> 1) - 1) & 1));      // the group has drained its previous tile
+          const bool ok = __shfl_sync(0xffffffffu, ok0 ? 1 : 0, 0) != 0;
           if (ok) {
             tc_fence_after();
             const uint32_t q_addr = smem_u32(smem + A5::OFF_Q + qb * A::Q_BYTES);
             const uint32_t k_addr = smem_u32(smem + A5::OFF_K + kb * A::KV_BYTES);
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + static_cast<uint32_t>(256 * u), make_desc_sw128(q_addr) + static_cast<uint64_t>(2 * k),
-                        make_desc_sw128(k_addr) + static_cast<uint64_t>(2 * k), idesc_s, k != 0 ? 1u : 0u);
-            umma_commit(&s_full[u]);
-            umma_commit(&q_empty[qb]);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base + static_cast<uint32_t>(256 * u), make_desc_sw128(q_addr) + static_cast<uint64_t>(2 * k),
+                          make_desc_sw128(k_addr) + static_cast<uint64_t>(2 * k), idesc_s, k != 0 ? 1u : 0u);
+              umma_commit(&s_full[u]);
+              umma_commit(&q_empty[qb]);
+            }
+            __syncwarp();
             ++nq;
             did = true;
           }
         }
         if (np < nq) {
           const int is = np / n_sub, t = np - is * n_sub, kb = is & 1, u = np & 1;
-          if (mbar_test(&p_full[u], (np >> 1) & 1)) {
+          const bool okp = __shfl_sync(0xffffffffu, mbar_test(&p_full[u], (np >> 1) & 1) ? 1 : 0, 0) != 0;
+          if (okp) {
             tc_fence_after();
             const uint32_t v_addr = smem_u32(smem + A5::OFF_V + kb * A::KV_BYTES);
+            if (elect_one_sync()) {
 #pragma unroll 1
-            for (int k = 0; k < pv_steps; ++k)
-              umma_bf16_ts(tmem_base + static_cast<uint32_t>(256 * u + 128), tmem_base + static_cast<uint32_t>(256 * u + 8 * k),
-                           make_desc(v_addr + static_cast<uint32_t>(k) * 2048u, 1024u, 1024u), idesc_pv, k != 0 ? 1u : 0u);
-            umma_commit(&o_full[u]);
-            if (t == n_sub - 1) umma_commit(&kv_empty[kb]);
+              for (int k = 0; k < pv_steps; ++k)
+                umma_bf16_ts(tmem_base + static_cast<uint32_t>(256 * u + 128), tmem_base + static_cast<uint32_t>(256 * u + 8 * k),
+                             make_desc(v_addr + static_cast<uint32_t>(k) * 2048u, 1024u, 1024u), idesc_pv, k != 0 ? 1u : 0u);
+              umma_commit(&o_full[u]);
+              if (t == n_sub - 1) umma_commit(&kv_empty[kb]);
+            }
+            __syncwarp();
             ++np;
             did = true;
           }

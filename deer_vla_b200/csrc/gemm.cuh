@@ -764,7 +764,7 @@ __device__ __forceinline__ void epi_tma_store_t(const GemmEpi& e, const CUtensor
     *reinterpret_cast<uint4*>(buf + lane * 64 + ((c ^ sw) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
   fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0) {
+  if (elect_one_sync()) {                                // the same leader lane every time (same member mask): it owns the bulk groups
     tma_store_2d(tmC, buf, col0, row0);
     tma_store_commit();
   }
@@ -931,7 +931,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int col0 = n_blk * G::BN + c * 32;
         if (epi.dbg != 2 && row0 < M && col0 < N) {
           if (epi.tma_store) {
-            if (lane == 0) tma_store_wait_read<1>();       // the store issued two chunks ago (same buffer) has read its tile
+            if (elect_one_sync()) tma_store_wait_read<1>(); // the store issued two chunks ago (same buffer) has read its tile
             __syncwarp();
             epi_tma_store(epi, &tmC, sc, row0, col0, v, obuf + ob * 2048, lane);
             ob ^= 1;
@@ -946,7 +946,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
   }
-  if (epi.tma_store && warp >= 2 && lane == 0) tma_store_wait_all();     // this thread's bulk stores have been written
+  if (epi.tma_store && warp >= 2) {
+    if (elect_one_sync()) tma_store_wait_all();         // the leader lane's bulk stores have been written
+    __syncwarp();
+  }
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) {
