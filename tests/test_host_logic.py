@@ -259,3 +259,18 @@ def test_head_key_canonicalisation_vs_reference_layouts():
         cfg = config_tiny(mlp_dims=(1024, 512, 256)[:nh], mlp_layernorm=a["mlp_layernorm"], lstm_layernorm=a["lstm_layernorm"])
         want = {"module." + n for n, _, _ in state_dict_spec(cfg) if n.startswith("extra_exit.")}
         assert set(canon) == want, (tag, sorted(set(canon) ^ want)[:6])
+
+
+def test_every_environment_switch_of_the_library_is_documented():
+    """INTEGRATION.md section 4 lists the library's environment switches; a getenv added to csrc/ without a row there fails here."""
+    import glob
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    for f in glob.glob(os.path.join(root, "deer_vla_b200", "csrc", "*.cu*")):
+        names |= set(re.findall(r'getenv\("([A-Z0-9_]+)"\)', open(f).read()))
+    assert names, "no getenv found: the scan is broken"
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, f"undocumented environment switches: {missing}"
